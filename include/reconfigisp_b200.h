@@ -1,0 +1,231 @@
+/*
+ * reconfigisp_b200 -- C ABI of the B200 (sm_100a) ISP hot path.
+ *
+ * The reference (yuke93/ReconfigISP) is pure Python; the arithmetic of its classical ISP
+ * stages lives behind the plugin call  Kernel().run(img, option, params_dict)  of five
+ * un-shipped modules (codes/models/modules/tools_origin.py:13-17) and in a handful of
+ * in-repo torch expressions.  This header is what an FFI binding for that path binds:
+ * plain pointers and sizes, no torch types.  Every entry point
+ *   - takes DEVICE pointers (fp32, NCHW planar, contiguous) unless the name ends in _host,
+ *   - never allocates: outputs and workspaces are caller-owned (query *_workspace()),
+ *   - enqueues on the given cudaStream_t (passed as void*), never synchronises,
+ *   - returns RISP_OK or a negative error code and never throws; risp_last_error() has text.
+ *
+ * Image conventions: Bayer = (N,1,H,W) RGGB, R=(0,0) G1=(0,1) G2=(1,0) B=(1,1)
+ * (srcnn_demosaic_arch.py:39-42); colour = (N,3,H,W) in B,G,R plane order (tools_origin.py:328-331).
+ */
+#ifndef RECONFIGISP_B200_H
+#define RECONFIGISP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RISP_ABI_VERSION 1
+
+typedef void* risp_stream_t; /* cudaStream_t */
+
+enum risp_status {
+  RISP_OK = 0,
+  RISP_E_INVALID = -1,     /* bad argument (maps to the reference's assert / ValueError) */
+  RISP_E_ALIGN = -2,       /* pointer / extent not aligned as the entry point documents */
+  RISP_E_CUDA = -3,        /* a CUDA runtime call failed */
+  RISP_E_UNSUPPORTED = -4, /* op has no such direction (maps to NotImplementedError) */
+  RISP_E_WORKSPACE = -5    /* workspace too small */
+};
+
+int risp_abi_version(void);
+const char* risp_last_error(void);
+int risp_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Per-pixel stage chain on BGR planes.
+ * One launch applies S <= RISP_MAX_STAGES per-pixel stages back to back in registers.
+ * With S == 1 it is the drop-in for one plugin call; longer chains are stage fusion for
+ * fixed pipelines (isp_universal.py:210-232 runs them as separate full-image passes).
+ *
+ * Stage parameters are KERNEL-level values (the [0,1]->range mappings of the wrappers,
+ * e.g. gain = p*5 tools_origin.py:214, P = p*10-5 :326, stay in the host language):
+ * ------------------------------------------------------------------------------------- */
+#define RISP_MAX_STAGES 6
+
+enum risp_op {
+  RISP_OP_SKIP = 0,      /* Skip                      tools_origin.py:256-262            P=0  */
+  RISP_OP_GAMMA = 1,     /* gamma 'manual'            :62-69   y=clamp(x,1e-8,1)^g       P=1  */
+  RISP_OP_GAIN = 2,      /* whitebalance 'manual'     :214-221 y_c=x_c*g_c               P=3  */
+  RISP_OP_GAIN_CLIP = 3, /* grayworld/whiteworld apply :35-41  y_c=clamp(x_c*g_c,0,1)    P=3  */
+  RISP_OP_POLY10 = 4,    /* WbQuadratic               :326-357 y_c=clamp(sum_k P[c][k]phi_k) P=30 */
+  RISP_OP_GTM = 5,       /* GtmManual(n_seg=iarg)     :425-438 piecewise-linear curve    P=iarg-1 */
+  RISP_OP_CCM = 6,       /* 3x3 colour matrix (north_star extension), clamp [0,1]        P=9  */
+  RISP_OP_REINHARD = 7,  /* globaltonemapping 'reinhard' :535  P=(a/Lavg, 1/w^2), fwd only    */
+  RISP_OP_CRYSIS = 8,    /* 'crysisengine'            :574     P=(1/lum_adapted), fwd only    */
+  RISP_OP_FILMIC = 9,    /* 'filmic'                  :615     P=(exposure, 1/f(w)), fwd only */
+  RISP_OP_COUNT = 10
+};
+
+/* Chain description, all HOST arrays of length S:
+ *   ops[s]       enum risp_op
+ *   param_off[s] offset of the stage's first parameter inside one parameter row
+ *   iarg[s]      integer argument (n_seg for RISP_OP_GTM, else 0)
+ * params: DEVICE, row n at params + n*param_stride; param_stride == 0 shares row 0 across
+ * the batch (the reference repeats one vector N times, super_prune...:208-209). */
+int risp_chain_fwd(const float* x, float* y, int N, long long HW, const int* ops, const int* param_off,
+                   const int* iarg, int S, const float* params, int param_stride, float in_scale,
+                   float out_scale, risp_stream_t stream);
+
+/* Backward of the chain: dx (nullable) and dparams.  dparams is (N,P) when param_stride==P and
+ * (1,P) when param_stride==0; it is fully overwritten.  Deterministic (no float atomics).
+ * Returns RISP_E_UNSUPPORTED if the chain holds a forward-only op. */
+size_t risp_chain_bwd_workspace(int N, long long HW, int P);
+int risp_chain_bwd(const float* x, const float* dy, float* dx, float* dparams, int N, long long HW,
+                   const int* ops, const int* param_off, const int* iarg, int S, const float* params,
+                   int param_stride, int P, void* workspace, size_t workspace_bytes, risp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Bayer-domain ops (bit-exact index work): RGGB pack / unpack and pixel shuffle
+ * (srcnn_demosaic_arch.py:39-43, path_14l_bayer_arch.py:71-75, nn.PixelShuffle(2) :48).
+ * ------------------------------------------------------------------------------------- */
+int risp_pack_rggb(const float* raw, float* packed, int N, int H, int W, risp_stream_t stream);
+int risp_unpack_rggb(const float* packed, float* raw, int N, int H, int W, risp_stream_t stream);
+/* (N, 4*C, H/2, W/2) <-> (N, C, H, W), channel c*4 + dy*2 + dx  (PixelShuffle(2) and its adjoint) */
+int risp_pixel_shuffle2(const float* in, float* out, int N, int C, int H, int W, risp_stream_t stream);
+int risp_pixel_unshuffle2(const float* in, float* out, int N, int C, int H, int W, risp_stream_t stream);
+
+/* Demosaic (demosaic.Demosaic().run, tools_origin.py:278-284,462-473,496-507). */
+enum risp_demosaic { RISP_DM_NEAREST = 0, RISP_DM_BILINEAR = 1, RISP_DM_MALVAR = 2 };
+/* y = clamp_hi? : MALVAR clips to [0, clip_hi] (8-bit output range of the wrapper). H, W even, W%4==0 */
+int risp_demosaic_fwd(const float* raw, float* bgr, int N, int H, int W, int kind, float clip_hi,
+                      risp_stream_t stream);
+/* adjoint: draw = J^T dbgr (for MALVAR the clip mask is recomputed from raw) */
+int risp_demosaic_bwd(const float* raw, const float* dbgr, float* draw, int N, int H, int W, int kind,
+                      float clip_hi, risp_stream_t stream);
+
+/* Bayer black-level + per-CFA-site gain (north_star extension; black level as in
+ * data/preprocessing/generate_rggb2bgr_imgs_SID_Sony.py:50):
+ *   y = clamp((max(x - bl, 0) / (1 - bl)) * gain[site], 0, 1);  params row = (bl, gR, gG1, gG2, gB) */
+int risp_bayer_blc_wb_fwd(const float* raw, float* out, int N, int H, int W, const float* params,
+                          int param_stride, risp_stream_t stream);
+size_t risp_bayer_blc_wb_bwd_workspace(int N, int H, int W);
+int risp_bayer_blc_wb_bwd(const float* raw, const float* dout, float* draw, float* dparams, int N, int H,
+                          int W, const float* params, int param_stride, void* workspace,
+                          size_t workspace_bytes, risp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused fixed pipeline (isp_universal.py:210-232 / origin_universal.py:143-161 as ONE pass):
+ *   raw --[blc/wb]--> demosaic(kind) --> per-pixel chain --> y        (16 B/px algorithmic)
+ * and the proxy-tuning step (isp_model.py:128-142) without materialising y:
+ *   loss = mean((y - gt)^2) ; dparams = d loss / d params              (32 B/px fwd+bwd)
+ * ------------------------------------------------------------------------------------- */
+int risp_pipeline_fwd(const float* raw, float* y, int N, int H, int W, int dm_kind, float dm_clip_hi,
+                      const int* ops, const int* param_off, const int* iarg, int S, const float* params,
+                      int param_stride, risp_stream_t stream);
+size_t risp_pipeline_step_workspace(int N, int H, int W, int P);
+/* loss_out: DEVICE float[1] (sum over all elements / (N*3*H*W)); dparams as in risp_chain_bwd;
+ * y_out nullable (written when the caller wants the image as well). */
+int risp_pipeline_mse_step(const float* raw, const float* gt, float* y_out, float* loss_out, float* dparams,
+                           int N, int H, int W, int dm_kind, float dm_clip_hi, const int* ops,
+                           const int* param_off, const int* iarg, int S, const float* params,
+                           int param_stride, int P, void* workspace, size_t workspace_bytes,
+                           risp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Per-image statistics (grayworld tools_origin.py:35-41, SRCNNRes global features
+ * srcnn_res_arch.py:36-40, whiteworld :655-662, conditional-module histogram :120-129).
+ * ------------------------------------------------------------------------------------- */
+size_t risp_plane_stats_workspace(int planes, long long HW);
+/* out: (planes, 3) = min, mean, max of every plane */
+int risp_plane_stats(const float* x, float* out, int planes, long long HW, void* workspace,
+                     size_t workspace_bytes, risp_stream_t stream);
+/* out: (N,) mean over pixels of log(1e-6 + lum(scale*x)) for BGR images (reinhard) */
+int risp_loglum_mean(const float* x, float* out, int N, long long HW, float scale, void* workspace,
+                     size_t workspace_bytes, risp_stream_t stream);
+/* torch.histc(plane, bins, 0, 1) per plane; out (planes, bins) float counts */
+int risp_histc01(const float* x, float* out, int planes, long long HW, int bins, risp_stream_t stream);
+/* exact k-th largest value per plane (radix select); k: DEVICE int64 (planes,), 1-based.
+ * workspace >= risp_kth_largest_workspace(planes) */
+size_t risp_kth_largest_workspace(int planes);
+int risp_kth_largest(const float* x, const long long* k, float* out, int planes, long long HW,
+                     void* workspace, size_t workspace_bytes, risp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Stencil stages on BGR images (spatialnoisereduction.run tools_origin.py:696-710,742-751;
+ * guided filter / sharpening are north_star extensions).  Shared-memory halo tiles.
+ * ------------------------------------------------------------------------------------- */
+/* window/sigma_color/sigma_space: DEVICE per-image arrays (window: int32, odd, <= 15) */
+/* max_window: HOST upper bound of window[] (sizes the halo tile); larger device values are clamped */
+int risp_bilateral_fwd(const float* x, float* y, int N, int H, int W, const int* window,
+                       const float* sigma_color, const float* sigma_space, int max_window,
+                       risp_stream_t stream);
+int risp_median_fwd(const float* x, float* y, int N, int H, int W, int size, risp_stream_t stream);
+int risp_guided_fwd(const float* x, float* y, int N, int H, int W, int radius, float eps, void* workspace,
+                    size_t workspace_bytes, risp_stream_t stream);
+size_t risp_guided_workspace(int N, int H, int W);
+/* unsharp mask, 5x5 binomial: y = clamp(x + amount[n]*(x - blur(x)), 0, 1) */
+int risp_sharpen_fwd(const float* x, float* y, int N, int H, int W, const float* amount,
+                     risp_stream_t stream);
+size_t risp_sharpen_bwd_workspace(int N, int H, int W);
+int risp_sharpen_bwd(const float* x, const float* dy, float* dx, float* damount, int N, int H, int W,
+                     const float* amount, void* workspace, size_t workspace_bytes, risp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * DARTS mixed-op (super_prune_fifteen_demos_four_bayer_two.py:185-212).
+ * ------------------------------------------------------------------------------------- */
+#define RISP_MAX_BRANCHES 16
+/* softmax(alpha) -> prune (< thr*max -> 0, mask from detached probs) -> / sum.detach()
+ * post: (K,) DEVICE; n_pruned: DEVICE int32[1].  All on device: no .item() sync (:193). */
+int risp_alpha_prune_fwd(const float* alpha, float* post, int* n_pruned, int K, float threshold,
+                         risp_stream_t stream);
+int risp_alpha_prune_bwd(const float* alpha, const float* dpost, float* dalpha, int K, float threshold,
+                         risp_stream_t stream);
+
+/* y = sum_j w[j]*f_j(x; params) + sum_i w[K_cls+i]*ext_i   on (N,3,HW) images.
+ *   cls_ops/cls_off/cls_iarg: K_cls classical single-stage branches evaluated in registers from x
+ *   ext: HOST array of K_ext DEVICE pointers to materialised candidate outputs (the CNN candidates)
+ *   w: DEVICE (K_cls+K_ext,) post-prune weights; a weight < 1e-9 skips the branch (:197) */
+int risp_mixed_fwd(const float* x, float* y, int N, long long HW, const int* cls_ops, const int* cls_off,
+                   const int* cls_iarg, int K_cls, const float* params, int param_stride,
+                   const float* const* ext, int K_ext, const float* w, risp_stream_t stream);
+size_t risp_mixed_bwd_workspace(int N, long long HW, int P, int K);
+/* dx (nullable): sum_j w_j J_j^T dy ; dw (K,): <dy, branch output> ; dparams as risp_chain_bwd
+ * (already scaled by w_j).  d ext_i = w_i * dy is left to the consumer (pass dy and w_i on). */
+int risp_mixed_bwd(const float* x, const float* dy, float* dx, float* dw, float* dparams, int N,
+                   long long HW, const int* cls_ops, const int* cls_off, const int* cls_iarg, int K_cls,
+                   const float* params, int param_stride, int P, const float* const* ext, int K_ext,
+                   const float* w, void* workspace, size_t workspace_bytes, risp_stream_t stream);
+
+/* Single-plane (Bayer-domain) mixed-op: n_skip Skip candidates + K_ext materialised candidates
+ * (the Bayer step: PathRestore14lBayer + Skip, super_prune...:57-74). */
+int risp_mixed1_fwd(const float* x, float* y, int N, long long HW, int n_skip, const float* const* ext,
+                    int K_ext, const float* w, risp_stream_t stream);
+int risp_mixed1_bwd(const float* x, const float* dy, float* dx, float* dw, int N, long long HW, int n_skip,
+                    const float* const* ext, int K_ext, const float* w, void* workspace,
+                    size_t workspace_bytes, risp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Loss (nn.MSELoss / nn.L1Loss, darts_model.py:60-65).  loss_out DEVICE float[1].
+ * ------------------------------------------------------------------------------------- */
+size_t risp_loss_workspace(long long numel);
+int risp_loss_fwd(const float* y, const float* gt, float* loss_out, long long numel, int l1, void* workspace,
+                  size_t workspace_bytes, risp_stream_t stream);
+/* dy = gscale[0] * d mean-loss / dy ;  gscale DEVICE float[1] (upstream gradient) */
+int risp_loss_bwd(const float* y, const float* gt, const float* gscale, float* dy, long long numel, int l1,
+                  risp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Patch split / merge (utils/util_path_restore.py:47-134) on device, NCHW.
+ * ------------------------------------------------------------------------------------- */
+/* tiles (T,C,h,w) from one frame (C,H,W); origins ys (ny), xs (nx) HOST int arrays, T = ny*nx */
+int risp_whole2patch(const float* frame, float* tiles, int C, int H, int W, int h, int w, const int* ys,
+                     int ny, const int* xs, int nx, risp_stream_t stream);
+/* frame = sum_t tile_t * mask / count_map, ramp mask (i+1)/(e+1), eh=(h-sh)/2, ew=(w-sw)/2;
+ * gather form (no atomics, deterministic).  clip01 != 0 also applies clip(.,0,1) (test_split.py:107) */
+int risp_patch2whole(const float* tiles, float* frame, int C, int H, int W, int h, int w, int sh, int sw,
+                     const int* ys, int ny, const int* xs, int nx, int clip01, risp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECONFIGISP_B200_H */

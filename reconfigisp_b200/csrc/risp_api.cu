@@ -1,0 +1,128 @@
+// Error plumbing, chain validation and the deterministic partial-sum finaliser.
+#include "risp_common.cuh"
+#include "risp_stage.cuh"
+
+#include <mutex>
+#include <string.h>
+
+namespace risp {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return RISP_E_CUDA;
+  }
+  return RISP_OK;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;  // B200
+  }
+  return n;
+}
+
+int op_param_count(int op, int iarg) {
+  switch (op) {
+    case RISP_OP_SKIP: return 0;
+    case RISP_OP_GAMMA: return 1;
+    case RISP_OP_GAIN: return 3;
+    case RISP_OP_GAIN_CLIP: return 3;
+    case RISP_OP_POLY10: return 30;
+    case RISP_OP_GTM: return iarg - 1;
+    case RISP_OP_CCM: return 9;
+    case RISP_OP_REINHARD: return 2;
+    case RISP_OP_CRYSIS: return 1;
+    case RISP_OP_FILMIC: return 2;
+    default: return -1;
+  }
+}
+
+bool op_has_bwd(int op) { return op >= RISP_OP_SKIP && op <= RISP_OP_CCM; }
+
+int make_chain(ChainDesc* d, const int* ops, const int* off, const int* iarg, int S, int* P_needed) {
+  RISP_REQUIRE(S >= 0 && S <= RISP_MAX_STAGES, RISP_E_INVALID, "chain length %d not in [0,%d]", S, RISP_MAX_STAGES);
+  RISP_REQUIRE(S == 0 || (ops && off && iarg), RISP_E_INVALID, "null chain description");
+  memset(d, 0, sizeof(*d));
+  d->S = S;
+  int need = 0, big = 0;
+  for (int s = 0; s < S; ++s) {
+    int cnt = op_param_count(ops[s], iarg[s]);
+    RISP_REQUIRE(cnt >= 0, RISP_E_INVALID, "stage %d: unknown op %d", s, ops[s]);
+    if (ops[s] == RISP_OP_GTM)
+      RISP_REQUIRE(iarg[s] >= 2 && iarg[s] <= 5, RISP_E_INVALID, "GTM n_seg %d not in [2,5]", iarg[s]);
+    RISP_REQUIRE(off[s] >= 0, RISP_E_INVALID, "stage %d: negative parameter offset", s);
+    big += op_is_big(ops[s]) ? 1 : 0;
+    d->op[s] = ops[s]; d->off[s] = off[s]; d->iarg[s] = iarg[s];
+    if (cnt > 0 && off[s] + cnt > need) need = off[s] + cnt;
+  }
+  RISP_REQUIRE(big <= 1, RISP_E_INVALID, "at most one POLY10/CCM stage per fused chain (got %d); split the chain", big);
+  if (P_needed) *P_needed = need;
+  return RISP_OK;
+}
+
+void chain_slot_list(const ChainDesc& d, SlotList* m) {
+  m->n = 0;
+  for (int s = 0; s < d.S; ++s) {
+    int cnt = op_param_count(d.op[s], d.iarg[s]);
+    for (int j = 0; j < cnt; ++j) {
+      m->dst[m->n] = (short)(d.off[s] + j);
+      m->slot[m->n] = (short)(op_is_big(d.op[s]) ? RISP_SLOT_BIG + j : s * RISP_SMALL_ACC + j);
+      m->n++;
+    }
+  }
+}
+
+// out[r][map.dst[e]] = scale * sum_b partial[(r*B + b)*NS + map.slot[e]]   (one warp per entry)
+struct SlotMap {
+  int n;
+  short dst[96];
+  short slot[96];
+};
+
+__global__ void finalize_kernel(const float* __restrict__ partial, float* __restrict__ out, int R, int B, int NS,
+                                int P, SlotMap map, float scale, int sum_rows) {
+  int e = blockIdx.x;
+  int r = blockIdx.y;
+  int lane = threadIdx.x;
+  float acc = 0.f;
+  int r0 = sum_rows ? 0 : r, r1 = sum_rows ? R : r + 1;
+  for (int rr = r0; rr < r1; ++rr)
+    for (int b = lane; b < B; b += 32) acc += partial[((long long)rr * B + b) * NS + map.slot[e]];
+  acc = warp_sum(acc);
+  if (lane == 0) out[(long long)(sum_rows ? 0 : r) * P + map.dst[e]] = acc * scale;
+}
+
+int finalize_partials(const float* partial, float* out, int R, int B, int NS, int P, const short* dst,
+                      const short* slot, int n, float scale, bool sum_rows, cudaStream_t st) {
+  RISP_REQUIRE(n <= 96, RISP_E_INVALID, "too many reduced entries (%d)", n);
+  if (n == 0) return RISP_OK;
+  SlotMap m;
+  m.n = n;
+  for (int i = 0; i < n; ++i) { m.dst[i] = dst[i]; m.slot[i] = slot[i]; }
+  dim3 grid(n, sum_rows ? 1 : R);
+  finalize_kernel<<<grid, 32, 0, st>>>(partial, out, R, B, NS, P, m, scale, sum_rows ? 1 : 0);
+  return check_launch("finalize_kernel");
+}
+
+}  // namespace risp
+
+extern "C" {
+int risp_abi_version(void) { return RISP_ABI_VERSION; }
+const char* risp_last_error(void) { return risp::g_err; }
+int risp_sm_count(void) { return risp::sm_count(); }
+}

@@ -1,0 +1,370 @@
+// Windowed stages on BGR images with shared-memory halo tiles:
+//   bilateral / median     spatialnoisereduction.run  (tools_origin.py:696-710, 742-751; OpenCV semantics)
+//   guided filter, sharpen north_star extensions (oracle/SPEC.md)
+// One CTA owns a 32x16 output tile of one image and stages the tile plus its halo for all three
+// planes in shared memory (coalesced row segments, border rule applied while loading), so every input
+// pixel is fetched from L2/HBM ~once and the window loops run out of shared memory.
+#include "risp_common.cuh"
+
+namespace risp {
+
+constexpr int TW = 32, TH = 16, kT = TW * TH;
+constexpr int kMaxR = 8;
+
+enum { BORDER_REFLECT101 = 0, BORDER_REPLICATE = 1 };
+
+__device__ __forceinline__ int border_idx(int i, int n, int mode) {
+  if (mode == BORDER_REPLICATE) return i < 0 ? 0 : (i >= n ? n - 1 : i);
+  // reflect-101, applied repeatedly for tiny images
+  while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+  return i;
+}
+
+// loads planes [0,C) of image n: tile origin (y0-R, x0-R), (TH+2R) x (TW+2R) floats per plane
+template <int C>
+__device__ __forceinline__ void load_tile(float* sh, const float* __restrict__ img, int H, int W, int y0, int x0, int R,
+                                          int mode, float scale) {
+  const int tw = TW + 2 * R, th = TH + 2 * R;
+  const long long plane = (long long)H * W;
+  for (int i = threadIdx.x; i < tw * th; i += kT) {
+    const int ly = i / tw, lx = i % tw;
+    const int gy = border_idx(y0 - R + ly, H, mode), gx = border_idx(x0 - R + lx, W, mode);
+#pragma unroll
+    for (int c = 0; c < C; ++c) sh[c * tw * th + i] = __ldg(img + c * plane + (long long)gy * W + gx) * scale;
+  }
+}
+
+// ---- bilateral ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kT)
+bilateral_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, const int* __restrict__ window,
+                 const float* __restrict__ sigma_color, const float* __restrict__ sigma_space, int Rmax) {
+  extern __shared__ float sh[];
+  const int n = blockIdx.z;
+  int R = window[n] / 2;
+  R = R < 0 ? 0 : (R > Rmax ? Rmax : R);
+  const float sc = sigma_color[n], ss = sigma_space[n];
+  const float kc = -0.5f / (sc * sc), ks = -0.5f / (ss * ss);
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  const long long plane = (long long)H * W;
+  const float* img = x + (long long)n * 3 * plane;
+  load_tile<3>(sh, img, H, W, y0, x0, R, BORDER_REFLECT101, 1.f);
+  __syncthreads();
+  const int tx = threadIdx.x % TW, ty = threadIdx.x / TW;
+  const int gx = x0 + tx, gy = y0 + ty;
+  if (gx >= W || gy >= H) return;
+  const int tw = TW + 2 * R, th = TH + 2 * R, ps = tw * th;
+  const float* c0 = sh + (ty + R) * tw + tx + R;
+  const float cb = c0[0], cg = c0[ps], cr = c0[2 * ps];
+  float nb = 0.f, ng = 0.f, nr = 0.f, den = 0.f;
+  const int R2 = R * R;
+  for (int dy = -R; dy <= R; ++dy) {
+    for (int dx = -R; dx <= R; ++dx) {
+      const int r2 = dy * dy + dx * dx;
+      if (r2 > R2) continue;   // circular support (cv2.bilateralFilter)
+      const float* q = c0 + dy * tw + dx;
+      const float vb = q[0], vg = q[ps], vr = q[2 * ps];
+      const float dist = fabsf(vb - cb) + fabsf(vg - cg) + fabsf(vr - cr);
+      const float wgt = __expf(dist * dist * kc + (float)r2 * ks);
+      nb = fmaf(wgt, vb, nb); ng = fmaf(wgt, vg, ng); nr = fmaf(wgt, vr, nr); den += wgt;
+    }
+  }
+  float* o = y + (long long)n * 3 * plane + (long long)gy * W + gx;
+  o[0] = nb / den; o[plane] = ng / den; o[2 * plane] = nr / den;
+}
+
+// ---- median ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cswap(float& a, float& b) { float t = fminf(a, b); b = fmaxf(a, b); a = t; }
+
+__device__ __forceinline__ float median9(float* v) {
+  // classic 19-exchange network (Paeth / Smith)
+  cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]); cswap(v[0], v[1]); cswap(v[3], v[4]); cswap(v[6], v[7]);
+  cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]); cswap(v[0], v[3]); cswap(v[5], v[8]); cswap(v[4], v[7]);
+  cswap(v[3], v[6]); cswap(v[1], v[4]); cswap(v[2], v[5]); cswap(v[4], v[7]); cswap(v[4], v[2]); cswap(v[6], v[4]);
+  cswap(v[4], v[2]);
+  return v[4];
+}
+
+__device__ __forceinline__ unsigned int okey(float f) {
+  unsigned int b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float okey_inv(unsigned int k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__global__ void __launch_bounds__(kT)
+median_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int R) {
+  extern __shared__ float sh[];
+  const long long plane = (long long)H * W;
+  const float* img = x + (long long)blockIdx.z * plane;     // one plane per z
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  load_tile<1>(sh, img, H, W, y0, x0, R, BORDER_REPLICATE, 1.f);
+  __syncthreads();
+  const int tx = threadIdx.x % TW, ty = threadIdx.x / TW;
+  const int gx = x0 + tx, gy = y0 + ty;
+  if (gx >= W || gy >= H) return;
+  const int tw = TW + 2 * R;
+  const float* c0 = sh + (ty + R) * tw + tx + R;
+  float out;
+  if (R == 1) {
+    float v[9];
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) v[(dy + 1) * 3 + dx + 1] = c0[dy * tw + dx];
+    out = median9(v);
+  } else {
+    // exact selection by bit-wise binary search on order-preserving keys: find the largest key K such
+    // that #(elements >= K) >= rank_from_top, i.e. the median element itself
+    const int cnt = (2 * R + 1) * (2 * R + 1);
+    const int need = cnt - cnt / 2;        // elements >= median (median is the (cnt/2)-th smallest, 0-based)
+    unsigned int key = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+      const unsigned int cand = key | (1u << bit);
+      int ge = 0;
+      for (int dy = -R; dy <= R; ++dy)
+        for (int dx = -R; dx <= R; ++dx) ge += (okey(c0[dy * tw + dx]) >= cand) ? 1 : 0;
+      if (ge >= need) key = cand;
+    }
+    out = okey_inv(key);
+  }
+  y[(long long)blockIdx.z * plane + (long long)gy * W + gx] = out;
+}
+
+// ---- guided filter (self-guided), two passes --------------------------------------------------------------
+__global__ void __launch_bounds__(kT)
+guided_ab_kernel(const float* __restrict__ x, float* __restrict__ a_out, float* __restrict__ b_out, int H, int W, int R,
+                 float eps) {
+  extern __shared__ float sh[];
+  const long long plane = (long long)H * W;
+  const float* img = x + (long long)blockIdx.z * plane;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  load_tile<1>(sh, img, H, W, y0, x0, R, BORDER_REFLECT101, 1.f);
+  __syncthreads();
+  const int tx = threadIdx.x % TW, ty = threadIdx.x / TW;
+  const int gx = x0 + tx, gy = y0 + ty;
+  if (gx >= W || gy >= H) return;
+  const int tw = TW + 2 * R;
+  const float* c0 = sh + (ty + R) * tw + tx + R;
+  float s = 0.f, s2 = 0.f;
+  for (int dy = -R; dy <= R; ++dy)
+    for (int dx = -R; dx <= R; ++dx) { float v = c0[dy * tw + dx]; s += v; s2 = fmaf(v, v, s2); }
+  const float inv = 1.f / (float)((2 * R + 1) * (2 * R + 1));
+  const float mean = s * inv, var = s2 * inv - mean * mean;
+  const float a = var / (var + eps);
+  const long long o = (long long)blockIdx.z * plane + (long long)gy * W + gx;
+  a_out[o] = a; b_out[o] = mean - a * mean;
+}
+
+__global__ void __launch_bounds__(kT)
+guided_out_kernel(const float* __restrict__ x, const float* __restrict__ a_in, const float* __restrict__ b_in,
+                  float* __restrict__ y, int H, int W, int R) {
+  extern __shared__ float sh[];
+  const long long plane = (long long)H * W;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  const int tw = TW + 2 * R, th = TH + 2 * R;
+  load_tile<1>(sh, a_in + (long long)blockIdx.z * plane, H, W, y0, x0, R, BORDER_REFLECT101, 1.f);
+  load_tile<1>(sh + tw * th, b_in + (long long)blockIdx.z * plane, H, W, y0, x0, R, BORDER_REFLECT101, 1.f);
+  __syncthreads();
+  const int tx = threadIdx.x % TW, ty = threadIdx.x / TW;
+  const int gx = x0 + tx, gy = y0 + ty;
+  if (gx >= W || gy >= H) return;
+  const float* ca = sh + (ty + R) * tw + tx + R;
+  const float* cb = ca + tw * th;
+  float sa = 0.f, sb = 0.f;
+  for (int dy = -R; dy <= R; ++dy)
+    for (int dx = -R; dx <= R; ++dx) { sa += ca[dy * tw + dx]; sb += cb[dy * tw + dx]; }
+  const float inv = 1.f / (float)((2 * R + 1) * (2 * R + 1));
+  const long long o = (long long)blockIdx.z * plane + (long long)gy * W + gx;
+  y[o] = sa * inv * x[o] + sb * inv;
+}
+
+// ---- sharpen (unsharp mask, 5x5 binomial) ------------------------------------------------------------------
+__constant__ float kBinom[5] = {1.f / 16, 4.f / 16, 6.f / 16, 4.f / 16, 1.f / 16};
+
+__device__ __forceinline__ float blur5(const float* c0, int tw) {
+  float acc = 0.f;
+#pragma unroll
+  for (int dy = -2; dy <= 2; ++dy) {
+    float row = 0.f;
+#pragma unroll
+    for (int dx = -2; dx <= 2; ++dx) row = fmaf(kBinom[dx + 2], c0[dy * tw + dx], row);
+    acc = fmaf(kBinom[dy + 2], row, acc);
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(kT)
+sharpen_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, const float* __restrict__ amount) {
+  extern __shared__ float sh[];
+  const long long plane = (long long)H * W;
+  const int pl = blockIdx.z;                      // n*3 + c
+  const float a = amount[pl / 3];
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  load_tile<1>(sh, x + (long long)pl * plane, H, W, y0, x0, 2, BORDER_REFLECT101, 1.f);
+  __syncthreads();
+  const int tx = threadIdx.x % TW, ty = threadIdx.x / TW;
+  const int gx = x0 + tx, gy = y0 + ty;
+  if (gx >= W || gy >= H) return;
+  const int tw = TW + 4;
+  const float* c0 = sh + (ty + 2) * tw + tx + 2;
+  const float v = c0[0];
+  y[(long long)pl * plane + (long long)gy * W + gx] = sat01(fmaf(a, v - blur5(c0, tw), v));
+}
+
+// pass 1 of the backward: e = dy * [0 <= u <= 1], d amount partials = sum e * (x - blur(x))
+__global__ void __launch_bounds__(kT)
+sharpen_bwd_e_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ e_out,
+                     float* __restrict__ partial, int H, int W, const float* __restrict__ amount) {
+  extern __shared__ float sh[];
+  const long long plane = (long long)H * W;
+  const int pl = blockIdx.z;
+  const float a = amount[pl / 3];
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  load_tile<1>(sh, x + (long long)pl * plane, H, W, y0, x0, 2, BORDER_REFLECT101, 1.f);
+  __syncthreads();
+  const int tx = threadIdx.x % TW, ty = threadIdx.x / TW;
+  const int gx = x0 + tx, gy = y0 + ty;
+  float contrib = 0.f;
+  if (gx < W && gy < H) {
+    const int tw = TW + 4;
+    const float* c0 = sh + (ty + 2) * tw + tx + 2;
+    const float v = c0[0], hp = v - blur5(c0, tw);
+    const long long o = (long long)pl * plane + (long long)gy * W + gx;
+    const float e = dy[o] * in01(fmaf(a, hp, v));
+    e_out[o] = e;
+    contrib = e * hp;
+  }
+  __shared__ float red[kT / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  contrib = warp_sum(contrib);
+  if (lane == 0) red[wid] = contrib;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < kT / 32; ++w) s += red[w];
+    partial[((long long)pl * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = s;
+  }
+}
+
+// z(py,px) = sum_d k[d] * E[p - d] on the zero-extended e (used only for the folded border terms)
+__device__ float blur_zero_ext(const float* __restrict__ e, int H, int W, int py, int px) {
+  float acc = 0.f;
+  for (int dy = -2; dy <= 2; ++dy) {
+    const int yy = py - dy;
+    if (yy < 0 || yy >= H) continue;
+    for (int dx = -2; dx <= 2; ++dx) {
+      const int xx = px - dx;
+      if (xx < 0 || xx >= W) continue;
+      acc = fmaf(kBinom[dy + 2] * kBinom[dx + 2], e[(long long)yy * W + xx], acc);
+    }
+  }
+  return acc;
+}
+
+// pass 2: dx = (1+a) e - a * blur^T(e);  blur^T folds the reflect-101 padding back into the frame
+__global__ void __launch_bounds__(kT)
+sharpen_bwd_dx_kernel(const float* __restrict__ e, float* __restrict__ dx, int H, int W, const float* __restrict__ amount) {
+  const long long plane = (long long)H * W;
+  const int pl = blockIdx.z;
+  const float a = amount[pl / 3];
+  const float* ep = e + (long long)pl * plane;
+  const int gx = blockIdx.x * TW + threadIdx.x % TW, gy = blockIdx.y * TH + threadIdx.x / TW;
+  if (gx >= W || gy >= H) return;
+  // candidate pre-images of (gy,gx) under reflect-101 inside the padded domain [-2, n+2)
+  int ys[3], xs[3], ny = 0, nx = 0;
+  ys[ny++] = gy; xs[nx++] = gx;
+  if (gy >= 1 && gy <= 2) ys[ny++] = -gy;
+  if (gy <= H - 2 && gy >= H - 3) ys[ny++] = 2 * H - 2 - gy;
+  if (gx >= 1 && gx <= 2) xs[nx++] = -gx;
+  if (gx <= W - 2 && gx >= W - 3) xs[nx++] = 2 * W - 2 - gx;
+  float bt = 0.f;
+  for (int i = 0; i < ny; ++i)
+    for (int j = 0; j < nx; ++j) bt += blur_zero_ext(ep, H, W, ys[i], xs[j]);
+  const long long o = (long long)pl * plane + (long long)gy * W + gx;
+  dx[o] = fmaf(1.f + a, ep[(long long)gy * W + gx], -a * bt);
+}
+
+static dim3 tile_grid(int H, int W, int Z) { return dim3((unsigned)cdiv(W, TW), (unsigned)cdiv(H, TH), (unsigned)Z); }
+static size_t tile_smem(int R, int planes) { return sizeof(float) * (size_t)planes * (TW + 2 * R) * (TH + 2 * R); }
+
+}  // namespace risp
+
+using namespace risp;
+
+extern "C" int risp_bilateral_fwd(const float* x, float* y, int N, int H, int W, const int* window,
+                                  const float* sigma_color, const float* sigma_space, int max_window,
+                                  risp_stream_t stream) {
+  RISP_REQUIRE(x && y && window && sigma_color && sigma_space && N > 0 && H > 1 && W > 1, RISP_E_INVALID,
+               "risp_bilateral_fwd: bad arguments");
+  RISP_REQUIRE(max_window >= 1 && max_window <= 2 * kMaxR + 1 && (max_window & 1), RISP_E_INVALID,
+               "risp_bilateral_fwd: max_window %d must be odd and <= %d", max_window, 2 * kMaxR + 1);
+  RISP_REQUIRE(N <= 65535, RISP_E_INVALID, "risp_bilateral_fwd: batch too large");
+  const int R = max_window / 2;
+  bilateral_kernel<<<tile_grid(H, W, N), kT, tile_smem(R, 3), as_stream(stream)>>>(x, y, H, W, window, sigma_color,
+                                                                                sigma_space, R);
+  return check_launch("bilateral_kernel");
+}
+
+extern "C" int risp_median_fwd(const float* x, float* y, int N, int H, int W, int size, risp_stream_t stream) {
+  RISP_REQUIRE(x && y && N > 0 && H > 0 && W > 0, RISP_E_INVALID, "risp_median_fwd: bad arguments");
+  RISP_REQUIRE(size >= 3 && size <= 2 * kMaxR + 1 && (size & 1), RISP_E_INVALID,
+               "risp_median_fwd: size %d must be odd and in [3,%d]", size, 2 * kMaxR + 1);
+  RISP_REQUIRE((long long)N * 3 <= 65535, RISP_E_INVALID, "risp_median_fwd: batch too large");
+  const int R = size / 2;
+  median_kernel<<<tile_grid(H, W, N * 3), kT, tile_smem(R, 1), as_stream(stream)>>>(x, y, H, W, R);
+  return check_launch("median_kernel");
+}
+
+extern "C" size_t risp_guided_workspace(int N, int H, int W) {
+  return (N > 0 && H > 0 && W > 0) ? (size_t)2 * N * 3 * H * W * sizeof(float) : 0;
+}
+
+extern "C" int risp_guided_fwd(const float* x, float* y, int N, int H, int W, int radius, float eps, void* workspace,
+                               size_t workspace_bytes, risp_stream_t stream) {
+  RISP_REQUIRE(x && y && N > 0 && H > 1 && W > 1, RISP_E_INVALID, "risp_guided_fwd: bad arguments");
+  RISP_REQUIRE(radius >= 1 && radius <= kMaxR, RISP_E_INVALID, "risp_guided_fwd: radius %d not in [1,%d]", radius, kMaxR);
+  RISP_REQUIRE(workspace && workspace_bytes >= risp_guided_workspace(N, H, W), RISP_E_WORKSPACE,
+               "risp_guided_fwd: workspace too small");
+  RISP_REQUIRE((long long)N * 3 <= 65535, RISP_E_INVALID, "risp_guided_fwd: batch too large");
+  cudaStream_t st = as_stream(stream);
+  float* a = static_cast<float*>(workspace);
+  float* b = a + (size_t)N * 3 * H * W;
+  guided_ab_kernel<<<tile_grid(H, W, N * 3), kT, tile_smem(radius, 1), st>>>(x, a, b, H, W, radius, eps);
+  guided_out_kernel<<<tile_grid(H, W, N * 3), kT, tile_smem(radius, 2), st>>>(x, a, b, y, H, W, radius);
+  return check_launch("guided kernels");
+}
+
+extern "C" int risp_sharpen_fwd(const float* x, float* y, int N, int H, int W, const float* amount,
+                                risp_stream_t stream) {
+  RISP_REQUIRE(x && y && amount && N > 0 && H > 2 && W > 2, RISP_E_INVALID, "risp_sharpen_fwd: bad arguments");
+  RISP_REQUIRE((long long)N * 3 <= 65535, RISP_E_INVALID, "risp_sharpen_fwd: batch too large");
+  sharpen_fwd_kernel<<<tile_grid(H, W, N * 3), kT, tile_smem(2, 1), as_stream(stream)>>>(x, y, H, W, amount);
+  return check_launch("sharpen_fwd_kernel");
+}
+
+extern "C" size_t risp_sharpen_bwd_workspace(int N, int H, int W) {
+  if (N <= 0 || H <= 0 || W <= 0) return 0;
+  size_t tiles = (size_t)cdiv(W, TW) * cdiv(H, TH);
+  return ((size_t)N * 3 * H * W + (size_t)N * 3 * tiles) * sizeof(float);
+}
+
+extern "C" int risp_sharpen_bwd(const float* x, const float* dy, float* dx, float* damount, int N, int H, int W,
+                                const float* amount, void* workspace, size_t workspace_bytes, risp_stream_t stream) {
+  RISP_REQUIRE(x && dy && dx && damount && amount && N > 0 && H > 2 && W > 2, RISP_E_INVALID, "risp_sharpen_bwd: bad arguments");
+  RISP_REQUIRE(workspace && workspace_bytes >= risp_sharpen_bwd_workspace(N, H, W), RISP_E_WORKSPACE,
+               "risp_sharpen_bwd: workspace too small");
+  RISP_REQUIRE((long long)N * 3 <= 65535, RISP_E_INVALID, "risp_sharpen_bwd: batch too large");
+  cudaStream_t st = as_stream(stream);
+  float* e = static_cast<float*>(workspace);
+  float* partial = e + (size_t)N * 3 * H * W;
+  dim3 grid = tile_grid(H, W, N * 3);
+  const int tiles = grid.x * grid.y;
+  sharpen_bwd_e_kernel<<<grid, kT, tile_smem(2, 1), st>>>(x, dy, e, partial, H, W, amount);
+  sharpen_bwd_dx_kernel<<<grid, kT, 0, st>>>(e, dx, H, W, amount);
+  int rc = check_launch("sharpen_bwd kernels");
+  if (rc != RISP_OK) return rc;
+  // damount[n] = sum over the 3 planes x tiles of image n: rows = N, B = 3*tiles, one slot
+  const short zero = 0;
+  return finalize_partials(partial, damount, N, 3 * tiles, 1, 1, &zero, &zero, 1, 1.f, false, st);
+}

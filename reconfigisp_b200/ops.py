@@ -1,0 +1,593 @@
+"""torch.autograd wrappers over the C ABI (include/reconfigisp_b200.h).
+
+PyTorch is plumbing here: it owns device memory, streams and the autograd tape; every
+arithmetic step on an image happens in the hand-written sm_100a kernels.  All ops take
+CUDA fp32 NCHW tensors and raise on anything else (no CPU / eager fallback).
+"""
+import torch
+
+from . import _lib as L
+
+OP = {k[len('RISP_OP_'):].lower(): v for k, v in L.ENUMS.items() if k.startswith('RISP_OP_') and k != 'RISP_OP_COUNT'}
+DM = {'nearest': L.ENUMS['RISP_DM_NEAREST'], 'bilinear': L.ENUMS['RISP_DM_BILINEAR'], 'malvar': L.ENUMS['RISP_DM_MALVAR'],
+      'laplacian': L.ENUMS['RISP_DM_MALVAR']}
+MAX_STAGES = L.ENUMS['RISP_MAX_STAGES']
+_NPARAM = {'skip': 0, 'gamma': 1, 'gain': 3, 'gain_clip': 3, 'poly10': 30, 'ccm': 9, 'reinhard': 2, 'crysis': 1,
+           'filmic': 2}
+FWD_ONLY = ('reinhard', 'crysis', 'filmic')
+BIG = ('poly10', 'ccm')
+
+
+def n_params(op, iarg=0):
+    return iarg - 1 if op == 'gtm' else _NPARAM[op]
+
+
+def _img(t, C=None):
+    if torch.is_tensor(t) and not t.is_cuda:
+        raise RuntimeError('reconfigisp_b200 ops run on CUDA tensors only (no CPU fallback); got a %s tensor' % t.device)
+    if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32 and t.dim() == 4):
+        raise ValueError('expected a CUDA fp32 NCHW tensor, got %s' % (type(t).__name__ if not torch.is_tensor(t)
+                                                                      else (t.device, t.dtype, tuple(t.shape)),))
+    if C is not None and t.shape[1] != C:
+        raise ValueError('expected %d channels, got %d' % (C, t.shape[1]))
+    return t.contiguous()
+
+
+class Chain:
+    """A fused sequence of per-pixel stages: [(op_name, iarg)], parameters packed row-wise."""
+
+    def __init__(self, stages):
+        stages = [(s, 0) if isinstance(s, str) else tuple(s) for s in stages]
+        self.names = [s for s, _ in stages]
+        self.iargs = [i for _, i in stages]
+        self.counts = [n_params(s, i) for s, i in stages]
+        self.offsets, off = [], 0
+        for c in self.counts:
+            self.offsets.append(off)
+            off += c
+        self.P = off
+        self.S = len(stages)
+        if self.S > MAX_STAGES:
+            raise ValueError('a fused chain holds at most %d stages' % MAX_STAGES)
+        if sum(n in BIG for n in self.names) > 1:
+            raise ValueError('at most one poly10/ccm stage per fused chain')
+        self.differentiable = not any(n in FWD_ONLY for n in self.names)
+        self._ops = L.iarr([OP[n] for n in self.names])
+        self._off = L.iarr(self.offsets)
+        self._iarg = L.iarr(self.iargs)
+
+    def desc(self):
+        return self._ops, self._off, self._iarg, self.S
+
+
+def _param_table(params, N, P):
+    """(N,P) or (1,P)/(P,) -> contiguous table and the ABI row stride (0 = shared row)."""
+    if P == 0:
+        return None, 0
+    if params.dim() == 1:
+        params = params.view(1, -1)
+    assert params.shape[1] == P, 'chain needs %d parameters per row, got %d' % (P, params.shape[1])
+    assert params.shape[0] in (1, N), 'parameter rows must be 1 or the batch size'
+    params = params.contiguous().float()
+    return params, (0 if params.shape[0] == 1 else P)
+
+
+class _ChainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, params, chain, in_scale, out_scale):
+        x = _img(x, 3)
+        N, _, H, W = x.shape
+        tab, stride = _param_table(params, N, chain.P) if chain.P else (None, 0)
+        y = torch.empty_like(x)
+        L.call('risp_chain_fwd', L.ptr(x), L.ptr(y), N, H * W, *chain.desc(), L.ptr(tab), stride,
+               float(in_scale), float(out_scale), L.stream())
+        ctx.chain, ctx.stride, ctx.scales = chain, stride, (in_scale, out_scale)
+        ctx.pshape = None if params is None else params.shape
+        ctx.save_for_backward(x, tab)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        chain = ctx.chain
+        if not chain.differentiable:
+            raise NotImplementedError('chain %s holds a forward-only (Origin*) stage' % chain.names)
+        if ctx.scales != (1.0, 1.0):
+            raise NotImplementedError('backward of a scaled chain is not provided')
+        x, tab = ctx.saved_tensors
+        N, _, H, W = x.shape
+        dy = _img(dy, 3)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        P = chain.P
+        dpar = torch.empty((1 if ctx.stride == 0 else N, P), device=x.device, dtype=torch.float32) if P else None
+        ws = L.workspace(L.size('risp_chain_bwd_workspace', N, H * W, P), x.device)
+        L.call('risp_chain_bwd', L.ptr(x), L.ptr(dy), L.ptr(dx), L.ptr(dpar), N, H * W, *chain.desc(), L.ptr(tab),
+               ctx.stride, P, L.ptr(ws), ws.numel() * 4, L.stream())
+        if dpar is not None:
+            dpar = dpar.view(ctx.pshape)
+        return dx, dpar, None, None, None
+
+
+def chain_apply(x, chain, params=None, in_scale=1.0, out_scale=1.0):
+    """y = stages(x).  params: (N,P) | (1,P) | (P,) kernel-level parameters (or None when P == 0)."""
+    if chain.S == 0 or all(n == 'skip' for n in chain.names):
+        if in_scale == 1.0 and out_scale == 1.0:
+            return x
+    return _ChainFn.apply(x, params, chain, float(in_scale), float(out_scale))
+
+
+_SINGLE = {}
+
+
+def _single(op, iarg=0):
+    key = (op, iarg)
+    if key not in _SINGLE:
+        _SINGLE[key] = Chain([(op, iarg)])
+    return _SINGLE[key]
+
+
+def gamma(x, g): return chain_apply(x, _single('gamma'), g)
+def gain(x, g): return chain_apply(x, _single('gain'), g)
+def gain_clip(x, g): return chain_apply(x, _single('gain_clip'), g)
+def poly10(x, coef): return chain_apply(x, _single('poly10'), coef)
+def ccm(x, m): return chain_apply(x, _single('ccm'), m)
+def gtm(x, knots, n_seg=4): return chain_apply(x, _single('gtm', n_seg), knots)
+
+
+# ---- statistics ---------------------------------------------------------------------------------
+def plane_stats(x):
+    """(N,C,H,W) -> (N,C,3) [min, mean, max] per plane (no autograd)."""
+    x = _img(x)
+    N, C, H, W = x.shape
+    out = torch.empty((N, C, 3), device=x.device, dtype=torch.float32)
+    ws = L.workspace(L.size('risp_plane_stats_workspace', N * C, H * W), x.device)
+    L.call('risp_plane_stats', L.ptr(x), L.ptr(out), N * C, H * W, L.ptr(ws), ws.numel() * 4, L.stream())
+    return out
+
+
+def loglum_mean(x, scale=1.0):
+    x = _img(x, 3)
+    N, _, H, W = x.shape
+    out = torch.empty((N,), device=x.device, dtype=torch.float32)
+    ws = L.workspace(L.size('risp_plane_stats_workspace', N, H * W), x.device)
+    L.call('risp_loglum_mean', L.ptr(x), L.ptr(out), N, H * W, float(scale), L.ptr(ws), ws.numel() * 4, L.stream())
+    return out
+
+
+def histc01(x, bins):
+    """torch.histc(plane, bins, 0, 1) for every plane, on the device: (N,C,H,W) -> (N, C*bins)."""
+    x = _img(x)
+    N, C, H, W = x.shape
+    out = torch.empty((N, C * bins), device=x.device, dtype=torch.float32)
+    L.call('risp_histc01', L.ptr(x.detach()), L.ptr(out), N * C, H * W, int(bins), L.stream())
+    return out
+
+
+def kth_largest(x, k):
+    """Exact k-th largest value of every plane; k: int64 tensor (N,) or (N,C), 1-based."""
+    x = _img(x)
+    N, C, H, W = x.shape
+    k = k.to(device=x.device, dtype=torch.int64)
+    k = (k.view(N, 1).expand(N, C) if k.numel() == N else k.view(N, C)).contiguous()
+    out = torch.empty((N, C), device=x.device, dtype=torch.float32)
+    ws = L.workspace(L.size('risp_kth_largest_workspace', N * C), x.device)
+    L.call('risp_kth_largest', L.ptr(x), L.ptr(k), L.ptr(out), N * C, H * W, L.ptr(ws), ws.numel() * 4, L.stream())
+    return out
+
+
+class _GrayworldFn(torch.autograd.Function):
+    """y = clamp(x * g, 0, 1), g_c = mean(all)/mean_c  (oracle/SPEC.md; tools_origin.py:22-45).
+    Backward = one chain backward (dx_local, dg) + the rank-1 term through the means."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _img(x, 3)
+        m = plane_stats(x)[..., 1]                                   # (N,3)
+        mc = torch.clamp(m, min=1e-6)
+        g = (m.mean(dim=1, keepdim=True) / mc).contiguous()
+        y = _ChainFn.apply(x, g, _single('gain_clip'), 1.0, 1.0)
+        ctx.save_for_backward(x, g, m)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, g, m = ctx.saved_tensors
+        N, _, H, W = x.shape
+        dy = _img(dy, 3)
+        ch = _single('gain_clip')
+        dx = torch.empty_like(x)
+        dg = torch.empty((N, 3), device=x.device, dtype=torch.float32)
+        ws = L.workspace(L.size('risp_chain_bwd_workspace', N, H * W, 3), x.device)
+        L.call('risp_chain_bwd', L.ptr(x), L.ptr(dy), L.ptr(dx), L.ptr(dg), N, H * W, *ch.desc(), L.ptr(g), 3, 3,
+               L.ptr(ws), ws.numel() * 4, L.stream())
+        # g_c = mbar / max(m_c, eps), mbar = mean_c m_c  ->  dL/dm_j = sum_c dg_c/(3 mc_c) - dg_j mbar/mc_j^2 [m_j >= eps]
+        mc = torch.clamp(m, min=1e-6)
+        mbar = m.mean(dim=1, keepdim=True)
+        dm = (dg / mc).sum(dim=1, keepdim=True) / 3.0 - dg * mbar / (mc * mc) * (m >= 1e-6).float()
+        # rank-1 term: every pixel of plane j receives dm_j / (H*W); applied with one more chain pass
+        dx = _add_plane_constant(dx, dm / float(H * W))
+        return dx
+
+
+def _add_plane_constant(x, c):
+    """x[n,ch] += c[n,ch] in place (tiny torch op on a (N,3,1,1) broadcast -> one elementwise kernel)."""
+    return x.add_(c.view(c.shape[0], c.shape[1], 1, 1))
+
+
+def grayworld(x):
+    return _GrayworldFn.apply(x)
+
+
+# ---- tone operators (forward-only Origin* stages) ---------------------------------------------------
+def _hable(v):
+    A, B, C, D, E, F = 0.15, 0.50, 0.10, 0.20, 0.02, 0.30
+    return (v * (A * v + C * B) + D * E) / (v * (A * v + B) + D * F) - E / F
+
+
+def tone_reinhard(x, white_point, middle_grey, data_scale=1.0):
+    """x in [0, data_scale]; params (N,) device tensors in [0,1]  (tools_origin.py:513-550)."""
+    x = _img(x.detach(), 3)
+    lavg = torch.exp(loglum_mean(x, 1.0 / data_scale))
+    a = torch.clamp(middle_grey.float(), min=1e-3)
+    w = torch.clamp(white_point.float(), min=1e-3)
+    p = torch.stack([a / lavg, 1.0 / (w * w)], dim=1)
+    return chain_apply(x, _single('reinhard'), p, 1.0 / data_scale, data_scale)
+
+
+def tone_crysis(x, lum_adapted, data_scale=1.0):
+    p = (1.0 / torch.clamp(lum_adapted.float(), min=1e-3)).view(-1, 1)
+    return chain_apply(_img(x.detach(), 3), _single('crysis'), p, 1.0 / data_scale, data_scale)
+
+
+def tone_filmic(x, white_point, exposure_bias, data_scale=1.0):
+    w = torch.clamp(white_point.float(), min=1e-3)
+    p = torch.stack([exposure_bias.float(), 1.0 / _hable(w)], dim=1)
+    return chain_apply(_img(x.detach(), 3), _single('filmic'), p, 1.0 / data_scale, data_scale)
+
+
+def whiteworld(x, ratio, data_scale=1.0):
+    """k = ceil(ratio*HW)-th largest value per plane maps to white (oracle/SPEC.md)."""
+    x = _img(x.detach(), 3)
+    N, _, H, W = x.shape
+    hw = float(H * W)
+    k = torch.clamp(torch.ceil(ratio.float().view(N) * hw), 1, hw).to(torch.int64)
+    t = kth_largest(x, k)
+    g = 1.0 / torch.clamp(t / data_scale, min=1e-6)
+    return chain_apply(x, _single('gain_clip'), g, 1.0 / data_scale, data_scale)
+
+
+# ---- Bayer ----------------------------------------------------------------------------------------
+class _ShuffleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, up):
+        x = _img(x)
+        N, C, H, W = x.shape
+        ctx.up = up
+        if up:
+            assert C % 4 == 0
+            out = torch.empty((N, C // 4, H * 2, W * 2), device=x.device, dtype=torch.float32)
+            L.call('risp_pixel_shuffle2', L.ptr(x), L.ptr(out), N, C // 4, H * 2, W * 2, L.stream())
+        else:
+            out = torch.empty((N, C * 4, H // 2, W // 2), device=x.device, dtype=torch.float32)
+            L.call('risp_pixel_unshuffle2', L.ptr(x), L.ptr(out), N, C, H, W, L.stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        return _ShuffleFn.apply(d, not ctx.up), None
+
+
+def pixel_shuffle2(x): return _ShuffleFn.apply(x, True)
+def pixel_unshuffle2(x): return _ShuffleFn.apply(x, False)
+def pack_rggb(raw): return _ShuffleFn.apply(_img(raw, 1), False)
+def unpack_rggb(p): return _ShuffleFn.apply(_img(p, 4), True)
+
+
+class _DemosaicFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, raw, kind, clip_hi):
+        raw = _img(raw, 1)
+        N, _, H, W = raw.shape
+        out = torch.empty((N, 3, H, W), device=raw.device, dtype=torch.float32)
+        L.call('risp_demosaic_fwd', L.ptr(raw), L.ptr(out), N, H, W, DM[kind], float(clip_hi), L.stream())
+        ctx.kind, ctx.clip_hi = kind, clip_hi
+        ctx.save_for_backward(raw)
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        raw, = ctx.saved_tensors
+        N, _, H, W = raw.shape
+        d = _img(d, 3)
+        draw = torch.empty_like(raw)
+        L.call('risp_demosaic_bwd', L.ptr(raw), L.ptr(d), L.ptr(draw), N, H, W, DM[ctx.kind], float(ctx.clip_hi), L.stream())
+        return draw, None, None
+
+
+def demosaic(raw, kind, clip_hi=1.0):
+    return _DemosaicFn.apply(raw, kind, clip_hi)
+
+
+class _BlcWbFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, raw, params):
+        raw = _img(raw, 1)
+        N, _, H, W = raw.shape
+        tab, stride = _param_table(params, N, 5)
+        out = torch.empty_like(raw)
+        L.call('risp_bayer_blc_wb_fwd', L.ptr(raw), L.ptr(out), N, H, W, L.ptr(tab), stride, L.stream())
+        ctx.stride, ctx.pshape = stride, params.shape
+        ctx.save_for_backward(raw, tab)
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        raw, tab = ctx.saved_tensors
+        N, _, H, W = raw.shape
+        d = _img(d, 1)
+        draw = torch.empty_like(raw) if ctx.needs_input_grad[0] else None
+        dpar = torch.empty((1 if ctx.stride == 0 else N, 5), device=raw.device, dtype=torch.float32)
+        ws = L.workspace(L.size('risp_bayer_blc_wb_bwd_workspace', N, H, W), raw.device)
+        L.call('risp_bayer_blc_wb_bwd', L.ptr(raw), L.ptr(d), L.ptr(draw), L.ptr(dpar), N, H, W, L.ptr(tab), ctx.stride,
+               L.ptr(ws), ws.numel() * 4, L.stream())
+        return draw, dpar.view(ctx.pshape)
+
+
+def bayer_blc_wb(raw, params):
+    """params (N,5)|(1,5): black level, gains [R,G1,G2,B]."""
+    return _BlcWbFn.apply(raw, params)
+
+
+# ---- stencils ---------------------------------------------------------------------------------------
+def bilateral(x, window, sigma_color, sigma_space, max_window=None):
+    x = _img(x.detach(), 3)
+    N, _, H, W = x.shape
+    window = window.to(device=x.device, dtype=torch.int32).contiguous()
+    if max_window is None:
+        max_window = int(window.max().item())        # the only host sync; callers that know the bound pass it
+    y = torch.empty_like(x)
+    L.call('risp_bilateral_fwd', L.ptr(x), L.ptr(y), N, H, W, L.ptr(window), L.ptr(sigma_color.float().contiguous()),
+           L.ptr(sigma_space.float().contiguous()), int(max_window), L.stream())
+    return y
+
+
+def median(x, size):
+    x = _img(x.detach(), 3)
+    N, _, H, W = x.shape
+    y = torch.empty_like(x)
+    L.call('risp_median_fwd', L.ptr(x), L.ptr(y), N, H, W, int(size), L.stream())
+    return y
+
+
+def guided_filter(x, radius, eps):
+    x = _img(x.detach(), 3)
+    N, _, H, W = x.shape
+    y = torch.empty_like(x)
+    ws = L.workspace(L.size('risp_guided_workspace', N, H, W), x.device)
+    L.call('risp_guided_fwd', L.ptr(x), L.ptr(y), N, H, W, int(radius), float(eps), L.ptr(ws), ws.numel() * 4, L.stream())
+    return y
+
+
+class _SharpenFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, amount):
+        x = _img(x, 3)
+        N, _, H, W = x.shape
+        a = amount.float().reshape(N).contiguous()
+        y = torch.empty_like(x)
+        L.call('risp_sharpen_fwd', L.ptr(x), L.ptr(y), N, H, W, L.ptr(a), L.stream())
+        ctx.ashape = amount.shape
+        ctx.save_for_backward(x, a)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, a = ctx.saved_tensors
+        N, _, H, W = x.shape
+        dy = _img(dy, 3)
+        dx = torch.empty_like(x)
+        da = torch.empty((N,), device=x.device, dtype=torch.float32)
+        ws = L.workspace(L.size('risp_sharpen_bwd_workspace', N, H, W), x.device)
+        L.call('risp_sharpen_bwd', L.ptr(x), L.ptr(dy), L.ptr(dx), L.ptr(da), N, H, W, L.ptr(a), L.ptr(ws),
+               ws.numel() * 4, L.stream())
+        return dx, da.view(ctx.ashape)
+
+
+def sharpen(x, amount):
+    return _SharpenFn.apply(x, amount)
+
+
+# ---- loss -------------------------------------------------------------------------------------------
+class _LossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, gt, l1):
+        y, gt = y.contiguous(), gt.contiguous()
+        assert y.is_cuda and gt.is_cuda and y.shape == gt.shape
+        out = torch.empty((1,), device=y.device, dtype=torch.float32)
+        ws = L.workspace(L.size('risp_loss_workspace', y.numel()), y.device)
+        L.call('risp_loss_fwd', L.ptr(y), L.ptr(gt), L.ptr(out), y.numel(), int(l1), L.ptr(ws), ws.numel() * 4, L.stream())
+        ctx.l1 = l1
+        ctx.save_for_backward(y, gt)
+        return out.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        y, gt = ctx.saved_tensors
+        dy = torch.empty_like(y)
+        gs = g.reshape(1).float().contiguous()
+        L.call('risp_loss_bwd', L.ptr(y), L.ptr(gt), L.ptr(gs), L.ptr(dy), y.numel(), int(ctx.l1), L.stream())
+        return dy, None, None
+
+
+def mse_loss(y, gt): return _LossFn.apply(y, gt, False)
+def l1_loss(y, gt): return _LossFn.apply(y, gt, True)
+
+
+# ---- DARTS mixed-op ----------------------------------------------------------------------------------
+class _AlphaPruneFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, alpha, threshold, n_pruned_out):
+        a = alpha.detach().float().contiguous()
+        post = torch.empty_like(a)
+        L.call('risp_alpha_prune_fwd', L.ptr(a), L.ptr(post), L.ptr(n_pruned_out), a.numel(), float(threshold), L.stream())
+        ctx.threshold = threshold
+        ctx.save_for_backward(a)
+        return post
+
+    @staticmethod
+    def backward(ctx, dpost):
+        a, = ctx.saved_tensors
+        da = torch.empty_like(a)
+        L.call('risp_alpha_prune_bwd', L.ptr(a), L.ptr(dpost.contiguous()), L.ptr(da), a.numel(), float(ctx.threshold), L.stream())
+        return da, None, None
+
+
+def alpha_prune(alpha, threshold, n_pruned_out=None):
+    """softmax -> online prune -> renormalise (super_prune...:185-193), all on the device."""
+    return _AlphaPruneFn.apply(alpha, threshold, n_pruned_out)
+
+
+class _MixedFn(torch.autograd.Function):
+    """y = sum_j w_j f_j(x; params) + sum_i w_{K_cls+i} ext_i."""
+
+    @staticmethod
+    def forward(ctx, x, params, w, chain, n_ext, *ext):
+        C = x.shape[1]
+        x = _img(x, C)
+        N, _, H, W = x.shape
+        ext = [_img(e, C) for e in ext]
+        w = w.float().contiguous()
+        y = torch.empty_like(x)
+        if C == 3:
+            tab, stride = _param_table(params, N, chain.P) if chain.P else (None, 0)
+            L.call('risp_mixed_fwd', L.ptr(x), L.ptr(y), N, H * W, *chain.desc(), L.ptr(tab), stride,
+                   L.parr(ext), len(ext), L.ptr(w), L.stream())
+        else:
+            tab, stride = None, 0
+            L.call('risp_mixed1_fwd', L.ptr(x), L.ptr(y), N, H * W, chain.S, L.parr(ext), len(ext), L.ptr(w), L.stream())
+        ctx.chain, ctx.stride, ctx.C = chain, stride, C
+        ctx.pshape = None if params is None else params.shape
+        ctx.save_for_backward(x, tab, w, *ext)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, tab, w, *ext = ctx.saved_tensors
+        chain, C = ctx.chain, ctx.C
+        N, _, H, W = x.shape
+        dy = _img(dy, C)
+        K = chain.S + len(ext)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.empty((K,), device=x.device, dtype=torch.float32)
+        P = chain.P
+        dpar = torch.empty((1 if ctx.stride == 0 else N, P), device=x.device, dtype=torch.float32) if P else None
+        ws = L.workspace(L.size('risp_mixed_bwd_workspace', N, H * W, P, K), x.device)
+        if C == 3:
+            L.call('risp_mixed_bwd', L.ptr(x), L.ptr(dy), L.ptr(dx), L.ptr(dw), L.ptr(dpar), N, H * W, *chain.desc(),
+                   L.ptr(tab), ctx.stride, P, L.parr(ext), len(ext), L.ptr(w), L.ptr(ws), ws.numel() * 4, L.stream())
+        else:
+            L.call('risp_mixed1_bwd', L.ptr(x), L.ptr(dy), L.ptr(dx), L.ptr(dw), N, H * W, chain.S, L.parr(ext),
+                   len(ext), L.ptr(w), L.ptr(ws), ws.numel() * 4, L.stream())
+        if dpar is not None:
+            dpar = dpar.view(ctx.pshape)
+        # d ext_i = w_i * dy : a skipped branch (w < 1e-9) gets no gradient, like the reference's `continue`
+        dext = [scale_by_device(dy, w, chain.S + i) if ctx.needs_input_grad[5 + i] else None for i in range(len(ext))]
+        return (dx, dpar, dw, None, None, *dext)
+
+
+def scale_by_device(t, w, idx):
+    """t * w[idx] with w on the device (no host sync)."""
+    if t.shape[1] == 3:
+        return chain_apply(t, _single('gain'), w[idx].expand(3).reshape(1, 3))
+    return t * w[idx]
+
+
+def mixed_op(x, chain, params, w, ext=()):
+    """chain: `Chain` of the classical candidates (each one stage, evaluated from x in registers);
+    ext: materialised candidate outputs; w: (K_cls+K_ext,) post-prune weights on the device."""
+    return _MixedFn.apply(x, params, w, chain, len(ext), *ext)
+
+
+# ---- fused fixed pipeline ------------------------------------------------------------------------------
+def pipeline_fwd(raw, dm_kind, chain, params=None, clip_hi=1.0):
+    raw = _img(raw.detach(), 1)
+    N, _, H, W = raw.shape
+    tab, stride = _param_table(params.detach(), N, chain.P) if chain.P else (None, 0)
+    y = torch.empty((N, 3, H, W), device=raw.device, dtype=torch.float32)
+    L.call('risp_pipeline_fwd', L.ptr(raw), L.ptr(y), N, H, W, DM[dm_kind], float(clip_hi), *chain.desc(), L.ptr(tab),
+           stride, L.stream())
+    return y
+
+
+class PipelineStep:
+    """Pre-allocated state for repeated proxy-tuning steps on frames of one geometry."""
+
+    def __init__(self, N, H, W, dm_kind, chain, device, clip_hi=1.0, shared_row=True):
+        self.N, self.H, self.W, self.dm, self.chain, self.clip_hi = N, H, W, DM[dm_kind], chain, float(clip_hi)
+        self.stride = 0 if shared_row else chain.P
+        self.loss = torch.empty((1,), device=device, dtype=torch.float32)
+        self.dparams = torch.empty((1 if shared_row else N, max(1, chain.P)), device=device, dtype=torch.float32)
+        self.ws = L.workspace(L.size('risp_pipeline_step_workspace', N, H, W, chain.P), device)
+
+    def __call__(self, raw, gt, params, y_out=None):
+        """-> (loss (1,), dparams).  raw (N,1,H,W), gt (N,3,H,W), params (1|N, P) kernel-level."""
+        L.call('risp_pipeline_mse_step', L.ptr(raw), L.ptr(gt), L.ptr(y_out), L.ptr(self.loss), L.ptr(self.dparams),
+               self.N, self.H, self.W, self.dm, self.clip_hi, *self.chain.desc(), L.ptr(params), self.stride,
+               self.chain.P, L.ptr(self.ws), self.ws.numel() * 4, L.stream())
+        return self.loss, self.dparams
+
+
+class _PipelineMseFn(torch.autograd.Function):
+    """loss = mse(pipeline(raw; params), gt) with d loss / d params from the same single pass."""
+
+    @staticmethod
+    def forward(ctx, params, raw, gt, dm_kind, chain, clip_hi):
+        raw, gt = _img(raw, 1), _img(gt, 3)
+        N, _, H, W = raw.shape
+        tab, stride = _param_table(params, N, chain.P)
+        step = PipelineStep(N, H, W, dm_kind, chain, raw.device, clip_hi, shared_row=(stride == 0))
+        loss, dpar = step(raw, gt, tab)
+        ctx.pshape = params.shape
+        ctx.save_for_backward(dpar)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        dpar, = ctx.saved_tensors
+        return (dpar * g).view(ctx.pshape), None, None, None, None, None
+
+
+def pipeline_mse(params, raw, gt, dm_kind, chain, clip_hi=1.0):
+    return _PipelineMseFn.apply(params, raw, gt, dm_kind, chain, clip_hi)
+
+
+# ---- patches ----------------------------------------------------------------------------------------
+def patch_origins(L_, l, s):
+    """util_path_restore.py:88-89."""
+    return list(range(0, L_ - l, s)) + [L_ - l]
+
+
+def whole2patch(frame, size, stride):
+    """frame (C,H,W) or (1,C,H,W) CUDA -> tiles (T,C,h,w), positions [(y,x)]."""
+    f = frame[0] if frame.dim() == 4 else frame
+    f = f.contiguous()
+    C, H, W = f.shape
+    h, w = size
+    sh, sw = stride
+    assert sh <= h <= H and sw <= w <= W and C >= 1
+    ys, xs = patch_origins(H, h, sh), patch_origins(W, w, sw)
+    tiles = torch.empty((len(ys) * len(xs), C, h, w), device=f.device, dtype=torch.float32)
+    L.call('risp_whole2patch', L.ptr(f), L.ptr(tiles), C, H, W, h, w, L.iarr(ys), len(ys), L.iarr(xs), len(xs), L.stream())
+    return tiles, [(y, x) for y in ys for x in xs]
+
+
+def patch2whole(tiles, frame_hw, stride, clip01=False):
+    tiles = tiles.contiguous()
+    T, C, h, w = tiles.shape
+    H, W = frame_hw
+    sh, sw = stride
+    ys, xs = patch_origins(H, h, sh), patch_origins(W, w, sw)
+    assert T == len(ys) * len(xs)
+    out = torch.empty((C, H, W), device=tiles.device, dtype=torch.float32)
+    L.call('risp_patch2whole', L.ptr(tiles), L.ptr(out), C, H, W, h, w, sh, sw, L.iarr(ys), len(ys), L.iarr(xs), len(xs),
+           int(bool(clip01)), L.stream())
+    return out
