@@ -131,6 +131,14 @@ int risp_pipeline_mse_step(const float* raw, const float* gt, float* y_out, floa
                            int param_stride, int P, void* workspace, size_t workspace_bytes,
                            risp_stream_t stream);
 
+/* Backward of risp_pipeline_fwd for an upstream gradient dy (N,3,H,W): recomputes the forward from
+ * raw in registers (nothing was saved) and reduces d/dparams; 16 B/px.  No gradient w.r.t. raw: the
+ * containers never need one (candidate-net weights are frozen).  Workspace as above. */
+int risp_pipeline_bwd(const float* raw, const float* dy, float* dparams, int N, int H, int W, int dm_kind,
+                      float dm_clip_hi, const int* ops, const int* param_off, const int* iarg, int S,
+                      const float* params, int param_stride, int P, void* workspace, size_t workspace_bytes,
+                      risp_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * Per-image statistics (grayworld tools_origin.py:35-41, SRCNNRes global features
  * srcnn_res_arch.py:36-40, whiteworld :655-662, conditional-module histogram :120-129).

@@ -56,33 +56,73 @@ template <> struct V3<1> {
   }
 };
 
+template <int VEC> struct MixNpx { static constexpr int value = (VEC == 4) ? 4 : 2; };
+
+// load / store one pixel group of a C-plane image (C = 1 or 3; missing planes read as 0)
+template <int VEC>
+__device__ __forceinline__ void mix_load(Px<MixNpx<VEC>::value>& px, const float* __restrict__ p, long long HW, long long i,
+                                         int C) {
+  V3<VEC> t;
+  if (VEC == 4) {
+    t.load(p, HW, i, C);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { px.b[k] = t.v[0][k]; px.g[k] = t.v[1][k]; px.r[k] = t.v[2][k]; }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const long long e = 2 * i + k;
+      const bool ok = e < HW;
+      px.b[k] = ok ? p[e] : 0.f;
+      px.g[k] = (ok && C > 1) ? p[HW + e] : 0.f;
+      px.r[k] = (ok && C > 2) ? p[2 * HW + e] : 0.f;
+    }
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void mix_store(const Px<MixNpx<VEC>::value>& px, float* __restrict__ p, long long HW, long long i,
+                                          int C) {
+  if (VEC == 4) {
+    st_stream4(p + 4 * i, make_float4(px.b[0], px.b[1], px.b[2], px.b[3]));
+    if (C > 1) st_stream4(p + HW + 4 * i, make_float4(px.g[0], px.g[1], px.g[2], px.g[3]));
+    if (C > 2) st_stream4(p + 2 * HW + 4 * i, make_float4(px.r[0], px.r[1], px.r[2], px.r[3]));
+  } else {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const long long e = 2 * i + k;
+      if (e < HW) {
+        p[e] = px.b[k];
+        if (C > 1) p[HW + e] = px.g[k];
+        if (C > 2) p[2 * HW + e] = px.r[k];
+      }
+    }
+  }
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(kT, 2)
 mixed_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long HW, int C, MixDesc d,
                  const float* __restrict__ params, int pstride, const float* __restrict__ w) {
+  constexpr int NPX = MixNpx<VEC>::value;
   const int n = blockIdx.y;
   const float* __restrict__ prow = params + (long long)n * pstride;
   const long long img = (long long)n * C * HW;
   float wk[RISP_MAX_BRANCHES];
 #pragma unroll
   for (int k = 0; k < RISP_MAX_BRANCHES; ++k) wk[k] = (k < d.K_cls + d.K_ext) ? w[k] : 0.f;
-  const long long nvec = HW / VEC;
+  const long long nvec = (VEC == 4) ? HW / 4 : (HW + 1) / 2;
   for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < nvec; i += (long long)gridDim.x * kT) {
-    V3<VEC> X, Y;
-    X.load(x + img, HW, i, C);
+    Px<NPX> X, Y;
+    mix_load<VEC>(X, x + img, HW, i, C);
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) Y.v[c][k] = 0.f;
+    for (int k = 0; k < NPX; ++k) { Y.b[k] = 0.f; Y.g[k] = 0.f; Y.r[k] = 0.f; }
 #pragma unroll
     for (int j = 0; j < RISP_MAX_STAGES; ++j) {
       if (j < d.K_cls && !(wk[j] < 1e-9f)) {
+        Px<NPX> t = X;
+        stage_fwd(d.op[j], d.iarg[j], prow + d.off[j], t);
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-          float b = X.v[0][k], g = X.v[1][k], r = X.v[2][k];
-          stage_fwd(d.op[j], d.iarg[j], prow + d.off[j], b, g, r);
-          Y.v[0][k] = fmaf(wk[j], b, Y.v[0][k]); Y.v[1][k] = fmaf(wk[j], g, Y.v[1][k]);
-          Y.v[2][k] = fmaf(wk[j], r, Y.v[2][k]);
+        for (int k = 0; k < NPX; ++k) {
+          Y.b[k] = fmaf(wk[j], t.b[k], Y.b[k]); Y.g[k] = fmaf(wk[j], t.g[k], Y.g[k]); Y.r[k] = fmaf(wk[j], t.r[k], Y.r[k]);
         }
       }
     }
@@ -91,16 +131,16 @@ mixed_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long H
       if (e < d.K_ext) {
         const float we = wk[d.K_cls + e];
         if (!(we < 1e-9f)) {
-          V3<VEC> E;
-          E.load(d.ext[e] + img, HW, i, C);
+          Px<NPX> E;
+          mix_load<VEC>(E, d.ext[e] + img, HW, i, C);
 #pragma unroll
-          for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) Y.v[c][k] = fmaf(we, E.v[c][k], Y.v[c][k]);
+          for (int k = 0; k < NPX; ++k) {
+            Y.b[k] = fmaf(we, E.b[k], Y.b[k]); Y.g[k] = fmaf(we, E.g[k], Y.g[k]); Y.r[k] = fmaf(we, E.r[k], Y.r[k]);
+          }
         }
       }
     }
-    Y.store(y + img, HW, i, C);
+    mix_store<VEC>(Y, y + img, HW, i, C);
   }
 }
 
@@ -109,6 +149,7 @@ __global__ void __launch_bounds__(kT, 1)
 mixed_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx,
                  float* __restrict__ partial, long long HW, int C, MixDesc d, const float* __restrict__ params,
                  int pstride, const float* __restrict__ w) {
+  constexpr int NPX = MixNpx<VEC>::value;
   const int n = blockIdx.y;
   const float* __restrict__ prow = params + (long long)n * pstride;
   const long long img = (long long)n * C * HW;
@@ -116,56 +157,53 @@ mixed_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, floa
 #pragma unroll
   for (int k = 0; k < RISP_MAX_BRANCHES; ++k) { wk[k] = (k < d.K_cls + d.K_ext) ? w[k] : 0.f; dot[k] = 0.f; }
   float accS[RISP_MAX_STAGES][RISP_SMALL_ACC];
-  float accB[RISP_BIG_ACC];
+  float2 accB[RISP_BIG_ACC];
 #pragma unroll
   for (int s = 0; s < RISP_MAX_STAGES; ++s)
 #pragma unroll
     for (int j = 0; j < RISP_SMALL_ACC; ++j) accS[s][j] = 0.f;
 #pragma unroll
-  for (int k = 0; k < RISP_BIG_ACC; ++k) accB[k] = 0.f;
+  for (int k = 0; k < RISP_BIG_ACC; ++k) accB[k] = make_float2(0.f, 0.f);
 
-  const long long nvec = HW / VEC;
+  const long long nvec = (VEC == 4) ? HW / 4 : (HW + 1) / 2;
   for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < nvec; i += (long long)gridDim.x * kT) {
-    V3<VEC> X, G, DX;
-    X.load(x + img, HW, i, C);
-    G.load(dy + img, HW, i, C);
+    Px<NPX> X, G, DX;
+    mix_load<VEC>(X, x + img, HW, i, C);
+    mix_load<VEC>(G, dy + img, HW, i, C);
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) DX.v[c][k] = 0.f;
+    for (int k = 0; k < NPX; ++k) { DX.b[k] = 0.f; DX.g[k] = 0.f; DX.r[k] = 0.f; }
 #pragma unroll
     for (int j = 0; j < RISP_MAX_STAGES; ++j) {
       if (j < d.K_cls && !(wk[j] < 1e-9f)) {
+        Px<NPX> t = X;
+        stage_fwd(d.op[j], d.iarg[j], prow + d.off[j], t);
+        float a = 0.f;
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-          const float xb = X.v[0][k], xg = X.v[1][k], xr = X.v[2][k];
-          float b = xb, g = xg, r = xr;
-          stage_fwd(d.op[j], d.iarg[j], prow + d.off[j], b, g, r);
-          float db = G.v[0][k], dg = G.v[1][k], dr = G.v[2][k];
-          dot[j] = fmaf(db, b, fmaf(dg, g, fmaf(dr, r, dot[j])));
-          stage_bwd<BIG>(d.op[j], d.iarg[j], prow + d.off[j], xb, xg, xr, db, dg, dr, accS[j], accB);
-          DX.v[0][k] = fmaf(wk[j], db, DX.v[0][k]); DX.v[1][k] = fmaf(wk[j], dg, DX.v[1][k]);
-          DX.v[2][k] = fmaf(wk[j], dr, DX.v[2][k]);
+        for (int k = 0; k < NPX; ++k) a = fmaf(G.b[k], t.b[k], fmaf(G.g[k], t.g[k], fmaf(G.r[k], t.r[k], a)));
+        dot[j] += a;
+        Px<NPX> dd = G;
+        stage_bwd<NPX, BIG>(d.op[j], d.iarg[j], prow + d.off[j], X, dd, accS[j], accB);
+#pragma unroll
+        for (int k = 0; k < NPX; ++k) {
+          DX.b[k] = fmaf(wk[j], dd.b[k], DX.b[k]); DX.g[k] = fmaf(wk[j], dd.g[k], DX.g[k]); DX.r[k] = fmaf(wk[j], dd.r[k], DX.r[k]);
         }
       }
     }
 #pragma unroll
     for (int e = 0; e < RISP_MAX_BRANCHES; ++e) {
       if (e < d.K_ext && !(wk[d.K_cls + e] < 1e-9f)) {
-        V3<VEC> E;
-        E.load(d.ext[e] + img, HW, i, C);
+        Px<NPX> E;
+        mix_load<VEC>(E, d.ext[e] + img, HW, i, C);
         float a = 0.f;
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-          for (int k = 0; k < VEC; ++k) a = fmaf(G.v[c][k], E.v[c][k], a);
+        for (int k = 0; k < NPX; ++k) a = fmaf(G.b[k], E.b[k], fmaf(G.g[k], E.g[k], fmaf(G.r[k], E.r[k], a)));
         // dot[] is indexed with a runtime value only through this unrolled select
 #pragma unroll
         for (int q = 0; q < RISP_MAX_BRANCHES; ++q)
           if (q == d.K_cls + e) dot[q] += a;
       }
     }
-    if (dx) DX.store(dx + img, HW, i, C);
+    if (dx) mix_store<VEC>(DX, dx + img, HW, i, C);
   }
 
   // parameter gradients carry the branch weight (d/dp of w_j * f_j)
@@ -189,8 +227,8 @@ mixed_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, floa
     }
 #pragma unroll
   for (int k = 0; k < RISP_BIG_ACC; ++k) {
-    float v = BIG ? warp_sum(accB[k] * bigw) : 0.f;
-    if (lane == 0) red[wid][RISP_SLOT_BIG + k] = v;
+    float v0 = BIG ? warp_sum(accB[k].x * bigw) : 0.f, v1 = BIG ? warp_sum(accB[k].y * bigw) : 0.f;
+    if (lane == 0) { red[wid][RISP_SLOT_BIG + 2 * k] = v0; red[wid][RISP_SLOT_BIG + 2 * k + 1] = v1; }
   }
 #pragma unroll
   for (int k = 0; k < RISP_MAX_BRANCHES; ++k) {
@@ -208,7 +246,7 @@ mixed_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, floa
 }
 
 static int mix_blocks(int N, long long HW) {
-  long long nvec = (HW % 4 == 0) ? HW / 4 : HW;
+  long long nvec = (HW % 4 == 0) ? HW / 4 : (HW + 1) / 2;
   long long g = cdiv(nvec, kT);
   long long cap = (long long)sm_count() * 4 / (N > 0 ? N : 1);
   if (cap < 8) cap = 8;

@@ -72,8 +72,8 @@ __device__ __forceinline__ void row_finish(float (&dst)[4 + 2 * HL], const RawRo
 // w[j][i]: row r-HL+j, column c0-HL+i.  `odd` = row parity (warp-uniform).  c0 is even, so pixel k has
 // column parity k&1.   Sites: (even,even)=R (even,odd)=G1 (odd,even)=G2 (odd,odd)=B.
 template <int DM, int HL>
-__device__ __forceinline__ void demosaic4(const float (&w)[2 * HL + 1][4 + 2 * HL], bool odd, float clip_hi,
-                                          float (&B)[4], float (&G)[4], float (&R)[4]) {
+__device__ __forceinline__ void demosaic4(const float (&w)[2 * HL + 1][4 + 2 * HL], bool odd, float clip_hi, Px<4>& out) {
+  float (&B)[4] = out.b; float (&G)[4] = out.g; float (&R)[4] = out.r;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int x = HL + k;            // window column of the pixel
@@ -127,11 +127,15 @@ struct PipeArgs {
   int pstride;
   int H, W, rows_per_chunk;
   float clip_hi;
+  int gt_is_dy;       // MODE_STEP: `gt` holds dL/dy (container-level backward) instead of the target
 };
 
-template <int DM, int MODE, bool BIG>
+template <int DM, int MODE, unsigned SIG, bool BIGG>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 pipeline_kernel(PipeArgs a, ChainDesc d) {
+  using SG = Sig<SIG>;
+  constexpr int SMAX = SG::S;
+  constexpr bool BIG = SG::generic ? BIGG : SG::big_c();
   constexpr int HL = (DM == RISP_DM_MALVAR) ? 2 : 1;
   constexpr int WR = 2 * HL + 1, WC = 4 + 2 * HL;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -148,16 +152,16 @@ pipeline_kernel(PipeArgs a, ChainDesc d) {
   const float* __restrict__ gtb = (MODE == MODE_STEP) ? a.gt + (long long)n * 3 * plane : nullptr;
   float* __restrict__ yb = a.y ? a.y + (long long)n * 3 * plane : nullptr;
 
-  float accS[RISP_MAX_STAGES][RISP_SMALL_ACC];
-  float accB[RISP_BIG_ACC];
+  float accS[SMAX][RISP_SMALL_ACC];
+  float2 accB[RISP_BIG_ACC];
   float loss = 0.f;
   if (MODE == MODE_STEP) {
 #pragma unroll
-    for (int s = 0; s < RISP_MAX_STAGES; ++s)
+    for (int s = 0; s < SMAX; ++s)
 #pragma unroll
       for (int j = 0; j < RISP_SMALL_ACC; ++j) accS[s][j] = 0.f;
 #pragma unroll
-    for (int k = 0; k < RISP_BIG_ACC; ++k) accB[k] = 0.f;
+    for (int k = 0; k < RISP_BIG_ACC; ++k) accB[k] = make_float2(0.f, 0.f);
   }
 
   if (strip * kStripCols < W) {   // warp-uniform: the whole strip is outside the frame otherwise
@@ -169,14 +173,14 @@ pipeline_kernel(PipeArgs a, ChainDesc d) {
       row_finish<HL>(w[j], q, W, c0, active, lane);
     }
     row_issue<HL>(q, img, reflect101(ra + HL, H), W, c0, active, lane);
-    float4 gB, gG, gR;   // GT of the row being computed, fetched one row ahead
+    float4 gB = make_float4(0.f, 0.f, 0.f, 0.f), gG = gB, gR = gB;   // GT of the row being computed, fetched one row ahead
     if (MODE == MODE_STEP && active) {
       const long long o = (long long)ra * W + c0;
       gB = ld_stream4(gtb + o); gG = ld_stream4(gtb + plane + o); gR = ld_stream4(gtb + 2 * plane + o);
     }
     for (int r = ra; r < rb; ++r) {
       row_finish<HL>(w[WR - 1], q, W, c0, active, lane);
-      float4 tB = gB, tG = gG, tR = gR;
+      const float4 tB = gB, tG = gG, tR = gR;
       if (r + 1 < rb) {
         row_issue<HL>(q, img, reflect101(r + 1 + HL, H), W, c0, active, lane);
         if (MODE == MODE_STEP && active) {
@@ -184,44 +188,45 @@ pipeline_kernel(PipeArgs a, ChainDesc d) {
           gB = ld_stream4(gtb + o); gG = ld_stream4(gtb + plane + o); gR = ld_stream4(gtb + 2 * plane + o);
         }
       }
-      float Bv[4], Gv[4], Rv[4];
-      demosaic4<DM, HL>(w, (r & 1) != 0, a.clip_hi, Bv, Gv, Rv);
+      Px<4> px;
+      demosaic4<DM, HL>(w, (r & 1) != 0, a.clip_hi, px);
       if (MODE == MODE_FWD) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-#pragma unroll
-          for (int s = 0; s < RISP_MAX_STAGES; ++s)
-            if (s < d.S) stage_fwd(d.op[s], d.iarg[s], prow + d.off[s], Bv[k], Gv[k], Rv[k]);
-        }
+        for (int s = 0; s < SMAX; ++s)
+          if (SG::live(d, s)) stage_fwd(SG::op(d, s), SG::iarg(d, s), prow + d.off[s], px);
       } else {
+        Px<4> saved[SMAX];
+#pragma unroll
+        for (int s = 0; s < SMAX; ++s) {
+          if (SG::live(d, s)) {
+            saved[s] = px;
+            stage_fwd(SG::op(d, s), SG::iarg(d, s), prow + d.off[s], px);
+          }
+        }
         const float gtB[4] = {tB.x, tB.y, tB.z, tB.w}, gtG[4] = {tG.x, tG.y, tG.z, tG.w},
                     gtR[4] = {tR.x, tR.y, tR.z, tR.w};
+        Px<4> dd;
+        if (a.gt_is_dy) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float sb[RISP_MAX_STAGES], sg[RISP_MAX_STAGES], sr[RISP_MAX_STAGES];
-          float b = Bv[k], g = Gv[k], rr = Rv[k];
-#pragma unroll
-          for (int s = 0; s < RISP_MAX_STAGES; ++s) {
-            if (s < d.S) {
-              sb[s] = b; sg[s] = g; sr[s] = rr;
-              stage_fwd(d.op[s], d.iarg[s], prow + d.off[s], b, g, rr);
-            }
-          }
-          Bv[k] = b; Gv[k] = g; Rv[k] = rr;
+          for (int k = 0; k < 4; ++k) { dd.b[k] = gtB[k]; dd.g[k] = gtG[k]; dd.r[k] = gtR[k]; }
+        } else {
           // d loss / d y up to the constant 2/numel, applied by the finaliser
-          float db = active ? b - gtB[k] : 0.f, dg = active ? g - gtG[k] : 0.f, dr = active ? rr - gtR[k] : 0.f;
-          loss = fmaf(db, db, fmaf(dg, dg, fmaf(dr, dr, loss)));
 #pragma unroll
-          for (int s = RISP_MAX_STAGES - 1; s >= 0; --s)
-            if (s < d.S)
-              stage_bwd<BIG>(d.op[s], d.iarg[s], prow + d.off[s], sb[s], sg[s], sr[s], db, dg, dr, accS[s], accB);
+          for (int k = 0; k < 4; ++k) {
+            dd.b[k] = active ? px.b[k] - gtB[k] : 0.f; dd.g[k] = active ? px.g[k] - gtG[k] : 0.f;
+            dd.r[k] = active ? px.r[k] - gtR[k] : 0.f;
+            loss = fmaf(dd.b[k], dd.b[k], fmaf(dd.g[k], dd.g[k], fmaf(dd.r[k], dd.r[k], loss)));
+          }
         }
+#pragma unroll
+        for (int s = SMAX - 1; s >= 0; --s)
+          if (SG::live(d, s)) stage_bwd<4, BIG>(SG::op(d, s), SG::iarg(d, s), prow + d.off[s], saved[s], dd, accS[s], accB);
       }
       if (yb && active) {
         const long long o = (long long)r * W + c0;
-        st_stream4(yb + o, make_float4(Bv[0], Bv[1], Bv[2], Bv[3]));
-        st_stream4(yb + plane + o, make_float4(Gv[0], Gv[1], Gv[2], Gv[3]));
-        st_stream4(yb + 2 * plane + o, make_float4(Rv[0], Rv[1], Rv[2], Rv[3]));
+        st_stream4(yb + o, make_float4(px.b[0], px.b[1], px.b[2], px.b[3]));
+        st_stream4(yb + plane + o, make_float4(px.g[0], px.g[1], px.g[2], px.g[3]));
+        st_stream4(yb + 2 * plane + o, make_float4(px.r[0], px.r[1], px.r[2], px.r[3]));
       }
 #pragma unroll
       for (int j = 0; j < WR - 1; ++j)
@@ -238,14 +243,15 @@ pipeline_kernel(PipeArgs a, ChainDesc d) {
     for (int s = 0; s < RISP_MAX_STAGES; ++s) {
 #pragma unroll
       for (int j = 0; j < RISP_SMALL_ACC; ++j) {
-        float v = (s < d.S) ? warp_sum(accS[s][j]) : 0.f;
+        float v = 0.f;
+        if (s < SMAX) { if (SG::live(d, s)) v = warp_sum(accS[s < SMAX ? s : 0][j]); }
         if (lane == 0) out[s * RISP_SMALL_ACC + j] = v;
       }
     }
 #pragma unroll
     for (int k = 0; k < RISP_BIG_ACC; ++k) {
-      float v = BIG ? warp_sum(accB[k]) : 0.f;
-      if (lane == 0) out[RISP_SLOT_BIG + k] = v;
+      float v0 = BIG ? warp_sum(accB[k].x) : 0.f, v1 = BIG ? warp_sum(accB[k].y) : 0.f;
+      if (lane == 0) { out[RISP_SLOT_BIG + 2 * k] = v0; out[RISP_SLOT_BIG + 2 * k + 1] = v1; }
     }
     float v = warp_sum(loss);
     if (lane == 0) { out[RISP_SLOT_LOSS] = v; out[RISP_SLOT_LOSS + 1] = 0.f; }
@@ -279,8 +285,21 @@ static int launch_pipeline(const PipeArgs& a, const ChainDesc& d, int N, int dm_
   PipeArgs b = a;
   b.rows_per_chunk = g.rows_per_chunk;
   dim3 grid(g.strips_x, g.chunks, N), block(kWarpsPerBlock * 32);
-#define RISP_PIPE(DMK) do { if (big) pipeline_kernel<DMK, MODE, true><<<grid, block, 0, st>>>(b, d); \
-                            else pipeline_kernel<DMK, MODE, false><<<grid, block, 0, st>>>(b, d); } while (0)
+  const unsigned sig = chain_signature(d);
+  bool done = false;
+#define RISP_PIPE_SIG(DMK, SG)                                                       \
+  if (!done && sig == (SG)) {                                                        \
+    pipeline_kernel<DMK, MODE, (SG), false><<<grid, block, 0, st>>>(b, d);           \
+    done = true;                                                                     \
+  }
+#define RISP_PIPE(DMK)                                                               \
+  do {                                                                               \
+    RISP_PIPE_SIG(DMK, RISP_SIG_A) RISP_PIPE_SIG(DMK, RISP_SIG_B) RISP_PIPE_SIG(DMK, RISP_SIG_C) RISP_PIPE_SIG(DMK, RISP_SIG_D) \
+    if (!done) {                                                                     \
+      if (big) pipeline_kernel<DMK, MODE, 0u, true><<<grid, block, 0, st>>>(b, d);   \
+      else pipeline_kernel<DMK, MODE, 0u, false><<<grid, block, 0, st>>>(b, d);      \
+    }                                                                                \
+  } while (0)
   switch (dm_kind) {
     case RISP_DM_NEAREST: RISP_PIPE(RISP_DM_NEAREST); break;
     case RISP_DM_BILINEAR: RISP_PIPE(RISP_DM_BILINEAR); break;
@@ -288,6 +307,7 @@ static int launch_pipeline(const PipeArgs& a, const ChainDesc& d, int N, int dm_
     default: set_error("unknown demosaic kind %d", dm_kind); return RISP_E_INVALID;
   }
 #undef RISP_PIPE
+#undef RISP_PIPE_SIG
   return check_launch("pipeline_kernel");
 }
 
@@ -315,7 +335,7 @@ extern "C" int risp_pipeline_fwd(const float* raw, float* y, int N, int H, int W
   if (rc != RISP_OK) return rc;
   RISP_REQUIRE(P == 0 || params, RISP_E_INVALID, "risp_pipeline_fwd: chain needs %d parameters but params is null", P);
   RISP_REQUIRE(param_stride == 0 || param_stride >= P, RISP_E_INVALID, "risp_pipeline_fwd: param_stride %d < %d", param_stride, P);
-  PipeArgs a{raw, nullptr, y, nullptr, params, param_stride, H, W, 0, dm_clip_hi};
+  PipeArgs a{raw, nullptr, y, nullptr, params, param_stride, H, W, 0, dm_clip_hi, 0};
   return launch_pipeline<MODE_FWD>(a, d, N, dm_kind, false, as_stream(stream));
 }
 
@@ -331,48 +351,67 @@ extern "C" size_t risp_pipeline_step_workspace(int N, int H, int W, int P) {
   return (size_t)N * g.warps_per_image * RISP_NSLOT * sizeof(float);
 }
 
-extern "C" int risp_pipeline_mse_step(const float* raw, const float* gt, float* y_out, float* loss_out, float* dparams,
-                                      int N, int H, int W, int dm_kind, float dm_clip_hi, const int* ops,
-                                      const int* param_off, const int* iarg, int S, const float* params,
-                                      int param_stride, int P, void* workspace, size_t workspace_bytes,
-                                      risp_stream_t stream) {
-  int rc = check_frame("risp_pipeline_mse_step", raw, N, H, W);
+static int pipeline_step_impl(const char* who, bool gt_is_dy, const float* raw, const float* gt, float* y_out,
+                              float* loss_out, float* dparams, int N, int H, int W, int dm_kind, float dm_clip_hi,
+                              const int* ops, const int* param_off, const int* iarg, int S, const float* params,
+                              int param_stride, int P, void* workspace, size_t workspace_bytes, risp_stream_t stream) {
+  int rc = check_frame(who, raw, N, H, W);
   if (rc != RISP_OK) return rc;
-  RISP_REQUIRE(gt && aligned16(gt) && loss_out, RISP_E_ALIGN, "risp_pipeline_mse_step: gt/loss_out null or unaligned");
-  RISP_REQUIRE(!y_out || aligned16(y_out), RISP_E_ALIGN, "risp_pipeline_mse_step: y_out must be 16-byte aligned");
+  RISP_REQUIRE(gt && aligned16(gt) && (gt_is_dy || loss_out), RISP_E_ALIGN, "%s: gt/dy/loss_out null or unaligned", who);
+  RISP_REQUIRE(!y_out || aligned16(y_out), RISP_E_ALIGN, "%s: y_out must be 16-byte aligned", who);
   ChainDesc d;
   int Pn = 0;
   rc = make_chain(&d, ops, param_off, iarg, S, &Pn);
   if (rc != RISP_OK) return rc;
   bool big = false;
   for (int s = 0; s < S; ++s) {
-    RISP_REQUIRE(op_has_bwd(ops[s]), RISP_E_UNSUPPORTED, "risp_pipeline_mse_step: op %d is forward-only", ops[s]);
+    RISP_REQUIRE(op_has_bwd(ops[s]), RISP_E_UNSUPPORTED, "%s: op %d is forward-only", who, ops[s]);
     big = big || op_is_big(ops[s]);
   }
-  RISP_REQUIRE(Pn <= P, RISP_E_INVALID, "risp_pipeline_mse_step: chain needs %d parameters, P=%d", Pn, P);
-  RISP_REQUIRE(Pn == 0 || (params && dparams), RISP_E_INVALID, "risp_pipeline_mse_step: null params/dparams");
-  RISP_REQUIRE(param_stride == 0 || param_stride >= P, RISP_E_INVALID, "risp_pipeline_mse_step: param_stride %d < P %d", param_stride, P);
+  RISP_REQUIRE(Pn <= P, RISP_E_INVALID, "%s: chain needs %d parameters, P=%d", who, Pn, P);
+  RISP_REQUIRE(Pn == 0 || (params && dparams), RISP_E_INVALID, "%s: null params/dparams", who);
+  RISP_REQUIRE(param_stride == 0 || param_stride >= P, RISP_E_INVALID, "%s: param_stride %d < P %d", who, param_stride, P);
   size_t need = risp_pipeline_step_workspace(N, H, W, P);
-  RISP_REQUIRE(workspace && workspace_bytes >= need, RISP_E_WORKSPACE, "risp_pipeline_mse_step: workspace %zu < %zu",
-               workspace_bytes, need);
+  RISP_REQUIRE(workspace && workspace_bytes >= need, RISP_E_WORKSPACE, "%s: workspace %zu < %zu", who, workspace_bytes, need);
   cudaStream_t st = as_stream(stream);
   PipeGeom g = pipe_geometry(N, H, W);
   float* partial = static_cast<float*>(workspace);
-  PipeArgs a{raw, gt, y_out, partial, params, param_stride, H, W, 0, dm_clip_hi};
+  PipeArgs a{raw, gt, y_out, partial, params, param_stride, H, W, 0, dm_clip_hi, gt_is_dy ? 1 : 0};
   rc = launch_pipeline<MODE_STEP>(a, d, N, dm_kind, big, st);
   if (rc != RISP_OK) return rc;
   const double numel = (double)N * 3.0 * H * W;
-  const short loss_dst = 0, loss_slot = RISP_SLOT_LOSS;
-  rc = finalize_partials(partial, loss_out, N, g.warps_per_image, RISP_NSLOT, 1, &loss_dst, &loss_slot, 1,
-                         (float)(1.0 / numel), true, st);
-  if (rc != RISP_OK || P == 0) return rc;
+  if (!gt_is_dy) {
+    const short loss_dst = 0, loss_slot = RISP_SLOT_LOSS;
+    rc = finalize_partials(partial, loss_out, N, g.warps_per_image, RISP_NSLOT, 1, &loss_dst, &loss_slot, 1,
+                           (float)(1.0 / numel), true, st);
+    if (rc != RISP_OK) return rc;
+  }
+  if (P == 0) return RISP_OK;
   bool shared_row = (param_stride == 0);
   if (cudaMemsetAsync(dparams, 0, sizeof(float) * (size_t)P * (shared_row ? 1 : N), st) != cudaSuccess) {
-    set_error("risp_pipeline_mse_step: memset failed");
+    set_error("%s: memset failed", who);
     return RISP_E_CUDA;
   }
   SlotList m;
   chain_slot_list(d, &m);
   return finalize_partials(partial, dparams, N, g.warps_per_image, RISP_NSLOT, P, m.dst, m.slot, m.n,
-                           (float)(2.0 / numel), shared_row, st);
+                           gt_is_dy ? 1.f : (float)(2.0 / numel), shared_row, st);
+}
+
+extern "C" int risp_pipeline_mse_step(const float* raw, const float* gt, float* y_out, float* loss_out, float* dparams,
+                                      int N, int H, int W, int dm_kind, float dm_clip_hi, const int* ops,
+                                      const int* param_off, const int* iarg, int S, const float* params,
+                                      int param_stride, int P, void* workspace, size_t workspace_bytes,
+                                      risp_stream_t stream) {
+  return pipeline_step_impl("risp_pipeline_mse_step", false, raw, gt, y_out, loss_out, dparams, N, H, W, dm_kind,
+                            dm_clip_hi, ops, param_off, iarg, S, params, param_stride, P, workspace, workspace_bytes,
+                            stream);
+}
+
+extern "C" int risp_pipeline_bwd(const float* raw, const float* dy, float* dparams, int N, int H, int W, int dm_kind,
+                                 float dm_clip_hi, const int* ops, const int* param_off, const int* iarg, int S,
+                                 const float* params, int param_stride, int P, void* workspace, size_t workspace_bytes,
+                                 risp_stream_t stream) {
+  return pipeline_step_impl("risp_pipeline_bwd", true, raw, dy, nullptr, nullptr, dparams, N, H, W, dm_kind, dm_clip_hi,
+                            ops, param_off, iarg, S, params, param_stride, P, workspace, workspace_bytes, stream);
 }

@@ -12,57 +12,91 @@ namespace risp {
 
 constexpr int kThreads = 256;
 
-template <int VEC> struct Vec;
-template <> struct Vec<4> {
-  float v[4];
-  __device__ __forceinline__ void load(const float* p) { float4 t = ld_stream4(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
-  __device__ __forceinline__ void store(float* p) const { st_stream4(p, make_float4(v[0], v[1], v[2], v[3])); }
-};
-template <> struct Vec<1> {
-  float v[1];
-  __device__ __forceinline__ void load(const float* p) { v[0] = ld_stream1(p); }
-  __device__ __forceinline__ void store(float* p) const { *p = v[0]; }
+// A thread's pixel group: G vectors of VEC pixels from each plane (NPX = G*VEC, kept even for the
+// packed fp32 math; the scalar path pairs neighbouring pixels and masks the odd tail).
+template <int VEC, int G>
+struct Group {
+  static constexpr int NPX = (VEC == 1) ? 2 * G : VEC * G;
+  Px<NPX> px;
+  // element index of pixel k for vector slot i0 (+ g*stride)
+  __device__ __forceinline__ void load(const float* __restrict__ base, long long HW, long long i0, long long stride,
+                                       long long nvec, float scale) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const long long i = i0 + g * stride;
+      if (VEC == 4) {
+        if (i < nvec) {
+          const float4 b = ld_stream4(base + 4 * i), gg = ld_stream4(base + HW + 4 * i), r = ld_stream4(base + 2 * HW + 4 * i);
+          px.b[4 * g] = b.x * scale; px.b[4 * g + 1] = b.y * scale; px.b[4 * g + 2] = b.z * scale; px.b[4 * g + 3] = b.w * scale;
+          px.g[4 * g] = gg.x * scale; px.g[4 * g + 1] = gg.y * scale; px.g[4 * g + 2] = gg.z * scale; px.g[4 * g + 3] = gg.w * scale;
+          px.r[4 * g] = r.x * scale; px.r[4 * g + 1] = r.y * scale; px.r[4 * g + 2] = r.z * scale; px.r[4 * g + 3] = r.w * scale;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { px.b[4 * g + k] = 0.f; px.g[4 * g + k] = 0.f; px.r[4 * g + k] = 0.f; }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const long long e = 2 * i + k;
+          const bool ok = (i < nvec) && (e < HW);
+          px.b[2 * g + k] = ok ? base[e] * scale : 0.f;
+          px.g[2 * g + k] = ok ? base[HW + e] * scale : 0.f;
+          px.r[2 * g + k] = ok ? base[2 * HW + e] * scale : 0.f;
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void store(float* __restrict__ base, long long HW, long long i0, long long stride,
+                                        long long nvec, float scale) const {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const long long i = i0 + g * stride;
+      if (i >= nvec) continue;
+      if (VEC == 4) {
+        st_stream4(base + 4 * i, make_float4(px.b[4 * g] * scale, px.b[4 * g + 1] * scale, px.b[4 * g + 2] * scale, px.b[4 * g + 3] * scale));
+        st_stream4(base + HW + 4 * i, make_float4(px.g[4 * g] * scale, px.g[4 * g + 1] * scale, px.g[4 * g + 2] * scale, px.g[4 * g + 3] * scale));
+        st_stream4(base + 2 * HW + 4 * i, make_float4(px.r[4 * g] * scale, px.r[4 * g + 1] * scale, px.r[4 * g + 2] * scale, px.r[4 * g + 3] * scale));
+      } else {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const long long e = 2 * i + k;
+          if (e < HW) { base[e] = px.b[2 * g + k] * scale; base[HW + e] = px.g[2 * g + k] * scale; base[2 * HW + e] = px.r[2 * g + k] * scale; }
+        }
+      }
+    }
+  }
 };
 
-template <int VEC, int SMAX>
+// number of vector slots of a plane: VEC==4 -> HW/4 float4s ; VEC==1 -> ceil(HW/2) pixel pairs
+template <int VEC> __device__ __host__ __forceinline__ long long vec_slots(long long HW) { return VEC == 4 ? HW / 4 : (HW + 1) / 2; }
+
+template <int VEC, unsigned SIG>
 __global__ void __launch_bounds__(kThreads, 2)
 chain_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long HW, ChainDesc d,
                  const float* __restrict__ params, int pstride, float in_scale, float out_scale) {
+  using SG = Sig<SIG>;
+  constexpr int SMAX = SG::S;
   const int n = blockIdx.y;
   const float* __restrict__ prow = params + (long long)n * pstride;
   const float* xb = x + (long long)n * 3 * HW;
   float* yb = y + (long long)n * 3 * HW;
-  const long long nvec = HW / VEC;
+  const long long nvec = vec_slots<VEC>(HW);
   const long long stride = (long long)gridDim.x * kThreads;
-  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += 2 * stride) {
-    Vec<VEC> B[2], G[2], R[2];
-    bool has2 = (i + stride) < nvec;
-    B[0].load(xb + i * VEC); G[0].load(xb + HW + i * VEC); R[0].load(xb + 2 * HW + i * VEC);
-    if (has2) {
-      long long j = i + stride;
-      B[1].load(xb + j * VEC); G[1].load(xb + HW + j * VEC); R[1].load(xb + 2 * HW + j * VEC);
-    }
+  constexpr int G = 2;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += G * stride) {
+    Group<VEC, G> grp;
+    grp.load(xb, HW, i, stride, nvec, in_scale);
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (u == 1 && !has2) break;
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) {
-        float b = B[u].v[k] * in_scale, g = G[u].v[k] * in_scale, r = R[u].v[k] * in_scale;
-#pragma unroll
-        for (int s = 0; s < SMAX; ++s)
-          if (s < d.S) stage_fwd(d.op[s], d.iarg[s], prow + d.off[s], b, g, r);
-        B[u].v[k] = b * out_scale; G[u].v[k] = g * out_scale; R[u].v[k] = r * out_scale;
-      }
-      long long j = i + u * stride;
-      B[u].store(yb + j * VEC); G[u].store(yb + HW + j * VEC); R[u].store(yb + 2 * HW + j * VEC);
-    }
+    for (int s = 0; s < SMAX; ++s)
+      if (SG::live(d, s)) stage_fwd(SG::op(d, s), SG::iarg(d, s), prow + d.off[s], grp.px);
+    grp.store(yb, HW, i, stride, nvec, out_scale);
   }
 }
 
 // block-wide reduction of the per-thread accumulators into partial[(n*B + blockIdx.x)*NSLOT + slot]
 template <bool BIG, int SMAX>
 __device__ __forceinline__ void flush_accumulators(float (&accS)[SMAX][RISP_SMALL_ACC],
-                                                   float (&accB)[RISP_BIG_ACC], float extra,
+                                                   float2 (&accB)[RISP_BIG_ACC], float extra,
                                                    float* __restrict__ prow_out, int S, bool has_extra) {
   __shared__ float red[kThreads / 32][RISP_NSLOT];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -79,8 +113,8 @@ __device__ __forceinline__ void flush_accumulators(float (&accS)[SMAX][RISP_SMAL
   if (BIG) {
 #pragma unroll
     for (int k = 0; k < RISP_BIG_ACC; ++k) {
-      float v = warp_sum(accB[k]);
-      if (lane == 0) red[wid][RISP_SLOT_BIG + k] = v;
+      float v0 = warp_sum(accB[k].x), v1 = warp_sum(accB[k].y);
+      if (lane == 0) { red[wid][RISP_SLOT_BIG + 2 * k] = v0; red[wid][RISP_SLOT_BIG + 2 * k + 1] = v1; }
     }
   }
   if (has_extra) {
@@ -98,53 +132,51 @@ __device__ __forceinline__ void flush_accumulators(float (&accS)[SMAX][RISP_SMAL
   }
 }
 
-template <int VEC, bool BIG, int SMAX>
-__global__ void __launch_bounds__(kThreads, (BIG && SMAX > 3) ? 1 : 2)
+template <int VEC, unsigned SIG, bool BIGG>
+__global__ void __launch_bounds__(kThreads, (SIG == 0 && BIGG) ? 1 : 2)
 chain_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx,
                  float* __restrict__ partial, long long HW, ChainDesc d, const float* __restrict__ params,
                  int pstride) {
+  using SG = Sig<SIG>;
+  constexpr int SMAX = SG::S;
+  constexpr bool BIG = SG::generic ? BIGG : SG::big_c();
   const int n = blockIdx.y;
   const float* __restrict__ prow = params + (long long)n * pstride;
   const float* xb = x + (long long)n * 3 * HW;
   const float* gb = dy + (long long)n * 3 * HW;
   float* ob = dx ? dx + (long long)n * 3 * HW : nullptr;
   float accS[SMAX][RISP_SMALL_ACC];
-  float accB[RISP_BIG_ACC];
+  float2 accB[RISP_BIG_ACC];
 #pragma unroll
   for (int s = 0; s < SMAX; ++s)
 #pragma unroll
     for (int j = 0; j < RISP_SMALL_ACC; ++j) accS[s][j] = 0.f;
 #pragma unroll
-  for (int k = 0; k < RISP_BIG_ACC; ++k) accB[k] = 0.f;
+  for (int k = 0; k < RISP_BIG_ACC; ++k) accB[k] = make_float2(0.f, 0.f);
 
-  const long long nvec = HW / VEC;
+  const long long nvec = vec_slots<VEC>(HW);
   const long long stride = (long long)gridDim.x * kThreads;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += stride) {
-    Vec<VEC> B, G, R, DB, DG, DR;
-    B.load(xb + i * VEC); G.load(xb + HW + i * VEC); R.load(xb + 2 * HW + i * VEC);
-    DB.load(gb + i * VEC); DG.load(gb + HW + i * VEC); DR.load(gb + 2 * HW + i * VEC);
+    Group<VEC, 1> X, D;
+    X.load(xb, HW, i, stride, nvec, 1.f);
+    D.load(gb, HW, i, stride, nvec, 1.f);      // out-of-range tail pixels get d = 0
+    constexpr int NPX = Group<VEC, 1>::NPX;
+    Px<NPX> saved[SMAX];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      float sb[SMAX], sg[SMAX], sr[SMAX];
-      float b = B.v[k], g = G.v[k], r = R.v[k];
-#pragma unroll
-      for (int s = 0; s < SMAX; ++s) {
-        if (s < d.S) {
-          sb[s] = b; sg[s] = g; sr[s] = r;
-          if (s + 1 < d.S) stage_fwd(d.op[s], d.iarg[s], prow + d.off[s], b, g, r);
-        }
+    for (int s = 0; s < SMAX; ++s) {
+      if (SG::live(d, s)) {
+        saved[s] = X.px;
+        if (SG::generic ? (s + 1 < d.S) : (s + 1 < SMAX)) stage_fwd(SG::op(d, s), SG::iarg(d, s), prow + d.off[s], X.px);
       }
-      float db = DB.v[k], dg = DG.v[k], dr = DR.v[k];
-#pragma unroll
-      for (int s = SMAX - 1; s >= 0; --s)
-        if (s < d.S)
-          stage_bwd<BIG>(d.op[s], d.iarg[s], prow + d.off[s], sb[s], sg[s], sr[s], db, dg, dr, accS[s], accB);
-      DB.v[k] = db; DG.v[k] = dg; DR.v[k] = dr;
     }
-    if (ob) { DB.store(ob + i * VEC); DG.store(ob + HW + i * VEC); DR.store(ob + 2 * HW + i * VEC); }
+#pragma unroll
+    for (int s = SMAX - 1; s >= 0; --s)
+      if (SG::live(d, s))
+        stage_bwd<NPX, BIG>(SG::op(d, s), SG::iarg(d, s), prow + d.off[s], saved[s], D.px, accS[s], accB);
+    if (ob) D.store(ob, HW, i, stride, nvec, 1.f);
   }
-  flush_accumulators<BIG, SMAX>(accS, accB, 0.f, partial + ((long long)n * gridDim.x + blockIdx.x) * RISP_NSLOT, d.S,
-                          false);
+  flush_accumulators<BIG, SMAX>(accS, accB, 0.f, partial + ((long long)n * gridDim.x + blockIdx.x) * RISP_NSLOT,
+                                SG::generic ? d.S : SMAX, false);
 }
 
 static int pick_grid(long long nvec, int N, int per_thread) {
@@ -157,7 +189,7 @@ static int pick_grid(long long nvec, int N, int per_thread) {
 }
 
 static int chain_bwd_blocks(int N, long long HW) {
-  long long nvec = (HW % 4 == 0) ? HW / 4 : HW;
+  long long nvec = (HW % 4 == 0) ? HW / 4 : (HW + 1) / 2;
   return pick_grid(nvec, N, 1);
 }
 
@@ -178,15 +210,23 @@ extern "C" int risp_chain_fwd(const float* x, float* y, int N, long long HW, con
   RISP_REQUIRE(N <= 65535, RISP_E_INVALID, "risp_chain_fwd: batch %d > 65535", N);
   bool vec = (HW % 4 == 0) && aligned16(x) && aligned16(y);
   cudaStream_t st = as_stream(stream);
-#define LAUNCH(V, SM) chain_fwd_kernel<V, SM><<<grid, kThreads, 0, st>>>(x, y, HW, d, params, param_stride, in_scale, out_scale)
+  const unsigned sig = chain_signature(d);
+  bool done = false;
   if (vec) {
     dim3 grid(pick_grid(HW / 4, N, 2), N);
-    if (S <= 1) LAUNCH(4, 1); else if (S <= 3) LAUNCH(4, 3); else LAUNCH(4, RISP_MAX_STAGES);
+#define RISP_TRY(SG)                                                                                                 \
+    if (!done && sig == (SG)) {                                                                                      \
+      chain_fwd_kernel<4, (SG)><<<grid, kThreads, 0, st>>>(x, y, HW, d, params, param_stride, in_scale, out_scale); \
+      done = true;                                                                                                   \
+    }
+    RISP_FOR_EACH_SINGLE_SIG(RISP_TRY)
+    RISP_FOR_EACH_CHAIN_SIG(RISP_TRY)
+#undef RISP_TRY
+    if (!done) chain_fwd_kernel<4, 0u><<<grid, kThreads, 0, st>>>(x, y, HW, d, params, param_stride, in_scale, out_scale);
   } else {
-    dim3 grid(pick_grid(HW, N, 2), N);
-    if (S <= 1) LAUNCH(1, 1); else LAUNCH(1, RISP_MAX_STAGES);
+    dim3 grid(pick_grid((HW + 1) / 2, N, 2), N);
+    chain_fwd_kernel<1, 0u><<<grid, kThreads, 0, st>>>(x, y, HW, d, params, param_stride, in_scale, out_scale);
   }
-#undef LAUNCH
   return check_launch("chain_fwd_kernel");
 }
 
@@ -221,12 +261,25 @@ extern "C" int risp_chain_bwd(const float* x, const float* dy, float* dx, float*
   int B = chain_bwd_blocks(N, HW);
   dim3 grid(B, N);
   float* partial = static_cast<float*>(workspace);
-#define LAUNCH(V, BG, SM) chain_bwd_kernel<V, BG, SM><<<grid, kThreads, 0, st>>>(x, dy, dx, partial, HW, d, params, param_stride)
-#define LAUNCH_S(V, BG) do { if (S <= 1) LAUNCH(V, BG, 1); else if (S <= 3) LAUNCH(V, BG, 3); else LAUNCH(V, BG, RISP_MAX_STAGES); } while (0)
-  if (vec) { if (big) LAUNCH_S(4, true); else LAUNCH_S(4, false); }
-  else     { if (big) LAUNCH(1, true, RISP_MAX_STAGES); else LAUNCH(1, false, RISP_MAX_STAGES); }
-#undef LAUNCH_S
-#undef LAUNCH
+  const unsigned sig = chain_signature(d);
+  bool done = false;
+  if (vec) {
+#define RISP_TRY(SG)                                                                                          \
+    if (!done && sig == (SG)) {                                                                               \
+      chain_bwd_kernel<4, (SG), false><<<grid, kThreads, 0, st>>>(x, dy, dx, partial, HW, d, params, param_stride); \
+      done = true;                                                                                            \
+    }
+    RISP_FOR_EACH_SINGLE_SIG(RISP_TRY)
+    RISP_FOR_EACH_CHAIN_SIG(RISP_TRY)
+#undef RISP_TRY
+    if (!done) {
+      if (big) chain_bwd_kernel<4, 0u, true><<<grid, kThreads, 0, st>>>(x, dy, dx, partial, HW, d, params, param_stride);
+      else chain_bwd_kernel<4, 0u, false><<<grid, kThreads, 0, st>>>(x, dy, dx, partial, HW, d, params, param_stride);
+    }
+  } else {
+    if (big) chain_bwd_kernel<1, 0u, true><<<grid, kThreads, 0, st>>>(x, dy, dx, partial, HW, d, params, param_stride);
+    else chain_bwd_kernel<1, 0u, false><<<grid, kThreads, 0, st>>>(x, dy, dx, partial, HW, d, params, param_stride);
+  }
   rc = check_launch("chain_bwd_kernel");
   if (rc != RISP_OK) return rc;
   if (P > 0) {
