@@ -1,0 +1,55 @@
+"""Data-parallel plumbing: one process per GPU, `torch.distributed` (NCCL over NVLink / NVSwitch).
+
+The only exchange step on this path is the all-reduce of the module-parameter and architecture-weight
+gradients: 216 floats = 864 B for n_step = 3.  It is latency-bound, so all gradients
+of one backward pass travel as ONE contiguous fp32 buffer in ONE collective.  (The reference reduces only
+the DDP-wrapped pass and leaves the alpha gradients rank-local; north_star asks for both.)"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """torchrun-style rendezvous (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*).  Returns (rank, world, local_rank)."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+        if backend == 'nccl':
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def is_dist():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def allreduce_mean_flat(tensors):
+    """Average a list of (small) gradient tensors across ranks with one collective.  None entries are
+    treated as zeros of unknown shape and returned as None (they are None on every rank alike)."""
+    if not is_dist():
+        return list(tensors)
+    live = [t for t in tensors if t is not None]
+    if not live:
+        return list(tensors)
+    flat = torch.cat([t.reshape(-1).float() for t in live])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat /= dist.get_world_size()
+    out, o = [], 0
+    for t in tensors:
+        if t is None:
+            out.append(None)
+        else:
+            out.append(flat[o:o + t.numel()].view_as(t))
+            o += t.numel()
+    return out
+
+
+def shard_batch(n_items, rank, world):
+    """Per-rank slice of a batch: batch_size // world_size items each (data/__init__.py:15-16)."""
+    per = n_items // world
+    return slice(rank * per, (rank + 1) * per)

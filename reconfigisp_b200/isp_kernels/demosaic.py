@@ -12,7 +12,7 @@ same stand-in the oracle uses -- see oracle/SPEC.md).
 import torch
 
 from reconfigisp_b200 import ops
-from ._common import nhwc_to_nchw, nchw_to_nhwc
+from reconfigisp_b200.isp_kernels._common import nhwc_to_nchw, nchw_to_nhwc
 
 _DEMOSAICNET = {'fn': None}
 

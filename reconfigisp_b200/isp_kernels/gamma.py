@@ -4,7 +4,7 @@
     one gamma per image (tools_origin.py:64-69, :181-194).
 """
 from reconfigisp_b200 import ops
-from ._common import nhwc_to_nchw, nchw_to_nhwc
+from reconfigisp_b200.isp_kernels._common import nhwc_to_nchw, nchw_to_nhwc
 
 
 class Gamma:

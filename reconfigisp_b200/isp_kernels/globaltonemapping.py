@@ -7,7 +7,7 @@
 The parameters stay on the device once uploaded; no device->host round trip is needed here.
 """
 from reconfigisp_b200 import ops
-from ._common import nhwc_to_nchw, nchw_to_nhwc, dev_vec
+from reconfigisp_b200.isp_kernels._common import nhwc_to_nchw, nchw_to_nhwc, dev_vec
 
 
 class GlobalToneMapping:

@@ -8,7 +8,7 @@
 import torch
 
 from reconfigisp_b200 import ops
-from ._common import nhwc_to_nchw, nchw_to_nhwc, dev_vec
+from reconfigisp_b200.isp_kernels._common import nhwc_to_nchw, nchw_to_nhwc, dev_vec
 
 
 class SpatialNoiseReduction:

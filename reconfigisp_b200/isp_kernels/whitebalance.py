@@ -7,7 +7,7 @@
 Arithmetic: sm_100a kernels behind include/reconfigisp_b200.h; definitions in oracle/SPEC.md.
 """
 from reconfigisp_b200 import ops
-from ._common import nhwc_to_nchw, nchw_to_nhwc, dev_vec
+from reconfigisp_b200.isp_kernels._common import nhwc_to_nchw, nchw_to_nhwc, dev_vec
 
 
 class WhiteBalance:

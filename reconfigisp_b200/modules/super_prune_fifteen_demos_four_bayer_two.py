@@ -1,0 +1,210 @@
+"""DARTS supernet with online pruning -- `SuperPruneFifteenDemosFourBayerTwo(n_step, threshold, module_path)`
+(codes/models/modules/super_prune_fifteen_demos_four_bayer_two.py:13-230): a Bayer step (2 candidates), a
+demosaic step (4) and `n_step` sRGB steps of 15 candidates each.  Same attributes (`all_modules`,
+`all_params`, `all_alphas`, `trainable_params`, `pruned_paths`, ...), properties and registered parameter
+names (`alpha_bayer`, `alpha_demosaic`, `alpha_step{k}`, `param_step{k}_{name}`).
+
+Mixed-op evaluation (reference :175-214) re-designed for the device:
+  * softmax / prune / renormalise of every step's alpha is a one-warp kernel; ONE device->host copy of
+    all post-prune weights per forward replaces the per-step `.item()` (:193) and the per-candidate
+    `if prob < 1e-9` syncs (:197) -- it is only needed to skip the CNN work of pruned candidates;
+  * the classical candidates of an sRGB step (gamma, grayworld, skip, wbmanual, wbquadratic, gtmmanual) are
+    evaluated in registers inside `ops.mixed_op` from a single read of x; only CNN candidates are
+    materialised; the weighted sum, all K alpha dot-products and the parameter gradients are one kernel each way;
+  * quirks kept: mask from detached probs and detached normaliser (:188-192), zero (not None) gradients for
+    the parameters of pruned candidates (:199-201), Skip aliasing, GtmManual using batch row 0.
+"""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from . import registry as R
+from . import tools_origin as T
+from . import tools_proxy as P
+
+SRGB_NAMES = R.NAMES['sRGB'][:R.N_SRGB_ORIGIN]
+# classical sRGB candidates evaluated in registers by the mixed-op kernel: (pool index, chain op)
+SRGB_CLASSICAL = [(0, ('gamma', 0)), (4, ('gain_clip', 0)), (9, ('skip', 0)), (10, ('gain', 0)), (12, ('poly10', 0)),
+                  (13, ('gtm', 4))]
+
+
+class _PlaneMeanFn(torch.autograd.Function):
+    """Per-plane mean with the broadcast backward (gray-world gains depend on the image)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape = x.shape
+        return ops.plane_stats(x)[..., 1].contiguous()
+
+    @staticmethod
+    def backward(ctx, dm):
+        N, C, H, W = ctx.shape
+        return (dm / float(H * W)).view(N, C, 1, 1).expand(N, C, H, W)
+
+
+def grayworld_gains(x):
+    m = _PlaneMeanFn.apply(x)
+    return m.mean(dim=1, keepdim=True) / torch.clamp(m, min=1e-6)
+
+
+class SuperPruneFifteenDemosFourBayerTwo(nn.Module):
+    def __init__(self, n_step, threshold, module_path, weight_seed=None):
+        super().__init__()
+        self.threshold = threshold
+        self.n_step = n_step
+        self.middle_results = None
+        self.pruned_paths = [0] * (n_step + 2)
+        seed = [weight_seed]
+
+        def net(name):
+            if seed[0] is None:
+                return R.build_net(name, module_path + R.PROXY_CKPT[name][1])
+            m = R.build_net(name, None, seed[0])
+            seed[0] += 1
+            return m
+
+        empty = lambda: nn.Parameter(torch.Tensor([]))
+        self.all_modules, self.all_params, self.all_alphas = [], [], []
+        self.trainable_params, self.param_and_alpha = [], []
+
+        # Bayer step (:57-74)
+        self.all_modules.append(nn.ModuleList([net('path_bayer'), T.Skip()]))
+        self.all_params.append(nn.ParameterList([empty(), empty()]))
+        self.alpha_bayer = nn.Parameter(torch.zeros((2,)))
+        self.all_alphas.append(self.alpha_bayer)
+        # demosaic step (:77-98)
+        self.all_modules.append(nn.ModuleList([T.DemosaicNearest(), net('bilinear'), net('laplacian'), T.DemosaicNet()]))
+        self.all_params.append(nn.ParameterList([empty() for _ in range(4)]))
+        self.alpha_demosaic = nn.Parameter(torch.zeros((4,)))
+        self.all_alphas.append(self.alpha_demosaic)
+        # sRGB steps (:101-171)
+        for k in range(n_step):
+            mods, pars = [], []
+            for name in SRGB_NAMES:
+                if name in R.CLASSICAL:
+                    mods.append(R.CLASSICAL[name]())
+                elif name == 'gtmmanual':
+                    mods.append(T.GtmManual(4))
+                else:
+                    mods.append(net(name))
+                logits = R.DEFAULT_LOGITS[name]
+                if len(logits):
+                    key = 'param_step{}_{}'.format(k + 1, name)
+                    setattr(self, key, nn.Parameter(torch.Tensor(logits)))
+                    pars.append(getattr(self, key))
+                else:
+                    pars.append(empty())
+            setattr(self, 'alpha_step{}'.format(k + 1), nn.Parameter(torch.zeros((15,))))
+            self.trainable_params += pars
+            self.all_modules.append(nn.ModuleList(mods))
+            self.all_params.append(nn.ParameterList(pars))
+            self.all_alphas.append(getattr(self, 'alpha_step{}'.format(k + 1)))
+        self.param_and_alpha = self.trainable_params + self.all_alphas
+        # like the reference, the per-step containers are plain Python lists: candidate-net weights stay out
+        # of named_parameters()/state_dict()/DDP
+        self._chain = ops.Chain([op for _, op in SRGB_CLASSICAL])
+
+    def _apply(self, fn, *a, **k):
+        super()._apply(fn, *a, **k)
+        for ml in self.all_modules:
+            ml._apply(fn, *a, **k)
+        return self
+
+    # ------------------------------------------------------------------------------------------------------
+    def _post_probs(self):
+        """post-prune weights of every step (device, differentiable) + one host copy for control flow."""
+        posts = [ops.alpha_prune(a, self.threshold) for a in self.all_alphas]
+        host = torch.cat([p.detach() for p in posts]).cpu()
+        out, o = [], 0
+        for i, p in enumerate(posts):
+            h = host[o:o + p.numel()]
+            o += p.numel()
+            self.pruned_paths[i] = int((h == 0).sum())
+            out.append((p, h))
+        return out
+
+    @staticmethod
+    def _dummy(par_list, idxs):
+        """0 * sum(params) of pruned candidates: zero instead of missing gradients (:199-201)."""
+        z = None
+        for i in idxs:
+            if par_list[i].nelement() > 0:
+                t = par_list[i].sum() * 0.0
+                z = t if z is None else z + t
+        return z
+
+    def forward(self, x):
+        """x: (N,1,H,W) RGGB -> (N,3,H,W) BGR."""
+        N = x.size(0)
+        self.middle_results = []
+        posts = self._post_probs()
+
+        # ---- Bayer step: [path_bayer, skip] -------------------------------------------------------------------
+        post, host = posts[0]
+        mods = self.all_modules[0]
+        ext, widx = [], [1]                                   # kernel order: [skip, materialised...]
+        if not host[0] < 1e-9:
+            ext.append(mods[0](x, None))
+            widx.append(0)
+        if host[1] < 1e-9:                                    # skip pruned: zero weight keeps the kernel generic
+            pass
+        y = ops.mixed_op(x, ops.Chain(['skip']), None, post[widx], ext)
+        self.middle_results.append(y)
+        x = y
+
+        # ---- demosaic step: every candidate maps 1 -> 3 planes, all are materialised ---------------------------
+        post, host = posts[1]
+        mods = self.all_modules[1]
+        ext, widx = [], []
+        for k in range(4):
+            if host[k] < 1e-9:
+                continue
+            ext.append(mods[k](x, None))
+            widx.append(k)
+        y = ops.mixed_op(ext[0].detach(), ops.Chain([]), None, post[widx], ext)
+        self.middle_results.append(y)
+        x = y
+
+        # ---- sRGB steps ----------------------------------------------------------------------------------------
+        cls_idx = [i for i, _ in SRGB_CLASSICAL]
+        for s in range(self.n_step):
+            post, host = posts[2 + s]
+            mods, pars = self.all_modules[2 + s], self.all_params[2 + s]
+            sig = lambda i: torch.sigmoid(pars[i]).view(1, -1)
+            # kernel-level parameter table of the classical candidates, one row per image
+            gw = grayworld_gains(x) if not host[4] < 1e-9 else torch.ones((N, 3), device=x.device)
+            table = torch.cat([sig(0).expand(N, 1), gw, (sig(10) * 5).expand(N, 3), (sig(12) * 10 - 5).expand(N, 30),
+                               sig(13).expand(N, 3)], dim=1)
+            ext, widx = [], list(cls_idx)
+            pruned = [i for i in range(15) if host[i] < 1e-9]
+            for i in range(15):
+                if i in cls_idx or host[i] < 1e-9:
+                    continue
+                par = pars[i]
+                par_tensor = None if par.nelement() == 0 else torch.sigmoid(par).repeat(N, 1)
+                ext.append(mods[i](x, par_tensor))
+                widx.append(i)
+            w = post[widx]
+            dummy = self._dummy(pars, pruned)
+            if dummy is not None:
+                w = w + dummy
+            y = ops.mixed_op(x, self._chain, table, w, ext)
+            self.middle_results.append(y)
+            x = y
+        return x
+
+    @property
+    def trainable_parameters(self):
+        return self.trainable_params
+
+    @property
+    def parameters_and_alpha(self):
+        return self.param_and_alpha
+
+    @property
+    def alphas(self):
+        return self.all_alphas
+
+    @property
+    def intermediate_results(self):
+        return self.middle_results

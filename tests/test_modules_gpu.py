@@ -1,0 +1,192 @@
+"""GPU parity of the module / container layer against the golden vectors recorded from the
+reference's own containers (oracle/gen_golden.py) and against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import isp_oracle as O            # noqa: E402
+from oracle import pipeline_oracle as PO      # noqa: E402
+
+T = torch.from_numpy
+
+
+def maxabs(a, b):
+    b = T(b) if isinstance(b, np.ndarray) else b
+    return float((a.detach().cpu().double() - b.detach().cpu().double()).abs().max())
+
+
+def relclose(a, b, rtol=2e-3, atol=1e-6):
+    b = T(b) if isinstance(b, np.ndarray) else b
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert float((a - b).abs().max()) <= atol + rtol * float(b.abs().max()), (float((a - b).abs().max()), float(b.abs().max()))
+
+
+def test_cnn_candidates_match_reference(golden):
+    from reconfigisp_b200.modules import tools_proxy as P
+    g = golden('cnn_candidates')
+    x3, raw = T(g['x3']).cuda().requires_grad_(), T(g['raw']).cuda().requires_grad_()
+    specs = [('srcnn_res3', P.ProxyNet(3, None), 10), ('srcnn_res1', P.ProxyNet(1, None), 11),
+             ('srcnn_demosaic', P.ProxyDemosaicNet(0, None), 12), ('path14l_bayer', P.PathRestore14lBayer(0, None), 13),
+             ('path14l_bgr', P.PathRestore14lBgr(0, None), 14)]
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for name, net, seed in specs:
+        net.load_state_dict(P.seeded_state_dict(net, seed))
+        net = net.cuda()
+        if name.startswith('srcnn_res'):
+            y = net(x3, T(g[name + '_par']).cuda()); inp = x3
+        elif name == 'path14l_bgr':
+            y = net(x3, None); inp = x3
+        else:
+            y = net(raw, None); inp = raw
+        dx, = torch.autograd.grad(y.square().sum(), inp)
+        assert maxabs(y, g[name + '_y']) <= 1e-4, name
+        relclose(dx, g[name + '_dx'], rtol=1e-3)
+        # state-dict keys are part of the API (tools_proxy.py load())
+        assert list(net.state_dict().keys()) == list(PO.seeded_weights(PO.ARCH_SHAPES[
+            {'srcnn_res3': 'srcnn_res', 'srcnn_res1': 'srcnn_res'}.get(name, name)](int(name[-1]) if name[-1].isdigit() else 0), 0).keys())
+
+
+ARCHS = (('classical', 'Bayer_02_Demosaic_02_sRGB_11_13_01'), ('sid', 'Bayer_01_Demosaic_03_sRGB_01_13_11'),
+         ('s7isp', 'Bayer_01_Demosaic_01_sRGB_04_01_13'), ('all_origin', 'Bayer_02_Demosaic_01_sRGB_05_02_03_04_06_07_08_10_12_15'))
+
+
+@pytest.mark.parametrize('fuse', [False, True])
+def test_origin_universal_matches_reference(golden, fuse):
+    from reconfigisp_b200.modules.origin_universal import OriginUniversal
+    g = golden('fixed_pipelines')
+    raw = T(g['raw']).cuda()
+    for tag, arch in ARCHS:
+        net = OriginUniversal('/x/', arch, weight_seed=10, fuse=fuse).cuda()
+        y = net(raw)
+        assert list(net.state_dict().keys()) == list(g[tag + '_keys']), tag
+        assert maxabs(y, g[tag + '_y']) <= 1e-4, (tag, maxabs(y, g[tag + '_y']))
+        inter = net.intermediate_results
+        assert len(inter) == len(net.all_modules)
+        for i in range(len(inter)):
+            assert maxabs(inter[i], g['%s_inter%d' % (tag, i)]) <= 1e-4, (tag, i)
+
+
+@pytest.mark.parametrize('fuse', [False, True])
+def test_isp_universal_grads_match_reference(golden, fuse):
+    from reconfigisp_b200.modules.isp_universal import IspUniversal
+    from reconfigisp_b200 import ops
+    g = golden('fixed_pipelines')
+    raw, gt = T(g['raw']).cuda(), T(g['isp_gt']).cuda()
+    net = IspUniversal('/x/', (None,) * 7, 'Bayer_02_Demosaic_01_sRGB_11_13_01_14_05', weight_seed=10, fuse=fuse).cuda()
+    assert list(net.state_dict().keys()) == list(g['isp_keys'])
+    y = net(raw)
+    assert maxabs(y, g['isp_y']) <= 1e-4
+    loss = ops.mse_loss(y, gt)
+    assert abs(float(loss.detach()) - float(g['isp_loss'])) <= 1e-6
+    nz = [(k, q) for k, q in net.named_parameters()]
+    grads = torch.autograd.grad(loss, [q for _, q in nz])
+    for (k, _), gr in zip(nz, grads):
+        relclose(gr, g['isp_dlogit_' + k])
+
+
+def test_isp_universal_state_dict_loads_into_origin(golden):
+    """S7ISP_test.yml:29-30: a checkpoint tuned with IspUniversal loads strict into OriginUniversal."""
+    from reconfigisp_b200.modules.isp_universal import IspUniversal
+    from reconfigisp_b200.modules.origin_universal import OriginUniversal
+    arch = 'Bayer_01_Demosaic_03_sRGB_01_13_11'
+    a = IspUniversal('/x/', (None,) * 5, arch, weight_seed=10)
+    b = OriginUniversal('/x/', arch, weight_seed=10)
+    b.load_state_dict(a.state_dict(), strict=True)
+    with pytest.raises(ValueError):
+        OriginUniversal('/x/', '01_02', weight_seed=1)
+    with pytest.raises(AssertionError):
+        OriginUniversal('/x/', 'sRGB_16', weight_seed=1)
+
+
+def test_supernet_matches_reference(golden):
+    from reconfigisp_b200.modules.super_prune_fifteen_demos_four_bayer_two import SuperPruneFifteenDemosFourBayerTwo
+    from reconfigisp_b200 import ops
+    g = golden('supernet')
+    net = SuperPruneFifteenDemosFourBayerTwo(int(g['n_step']), float(g['threshold']), '/x/', weight_seed=int(g['weight_seed'])).cuda()
+    names = [n for n, _ in net.named_parameters()]
+    assert names[:2] == ['alpha_bayer', 'alpha_demosaic'] and len(names) == 2 + 13 * int(g['n_step'])
+    with torch.no_grad():
+        for i, a in enumerate(net.alphas):
+            a.copy_(T(g['alpha%d' % i]))
+        for n, q in net.named_parameters():
+            if n.startswith('param_'):
+                q.copy_(T(g['logit_' + n]))
+    y = net(T(g['raw']).cuda())
+    assert net.pruned_paths == list(g['pruned'])
+    assert maxabs(y, g['y']) <= 1e-4
+    for i, m in enumerate(net.intermediate_results):
+        assert maxabs(m, g['inter%d' % i]) <= 1e-4, i
+    loss = ops.mse_loss(y, T(g['gt']).cuda())
+    assert abs(float(loss.detach()) - float(g['loss'])) <= 1e-6
+    nz = [q for q in net.trainable_parameters if q.nelement()]
+    grads = torch.autograd.grad(loss, list(net.alphas) + nz, allow_unused=True)
+    for i in range(len(net.alphas)):
+        relclose(grads[i], g['dalpha%d' % i], rtol=2e-3, atol=1e-7)
+    pnames = [n for n in names if n.startswith('param_')]
+    for n, gr in zip(pnames, grads[len(net.alphas):]):
+        assert gr is not None, n                               # dummy-gradient quirk: zeros, not None
+        relclose(gr, g['dlogit_' + n], rtol=2e-3, atol=1e-7)
+
+
+def test_conditional_module_matches_reference(golden):
+    from reconfigisp_b200.modules import tools_origin as TO
+    g = golden('cond_fc')
+    cm = TO.ConditionalWbManual(in_channels=(12, 5))
+    flat = T(g['flat']).cuda().requires_grad_()
+    out = cm._fc_forward(T(g['img']).cuda(), flat)
+    dflat, = torch.autograd.grad(out, flat, torch.ones_like(out))
+    assert maxabs(out, g['out']) <= 1e-6
+    relclose(dflat, g['dflat'], rtol=1e-4)
+    # and the full module against the oracle
+    img = T(g['img']).cuda().clamp(0, 1)
+    y = cm(img, flat)
+    yo = O.wb_manual(img.cpu(), T(g['out']) * 5) if False else None
+    p = O.fc_params(O.histc_planes(img.cpu(), 4), T(g['flat']), [12, 5, 3])
+    assert maxabs(y, O.wb_manual(img.cpu(), p * 5)) <= 1e-4
+
+
+def test_plugin_boundary_run_signatures():
+    """The five kernel modules resolve by bare name and honour the layouts of tools_origin.py."""
+    from reconfigisp_b200 import isp_kernels
+    isp_kernels.install()
+    import whitebalance, gamma, demosaic, globaltonemapping, spatialnoisereduction   # noqa: E401
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(2, 3, 16, 24, generator=g)
+    xd = x.cuda()
+    nhwc = xd.permute(0, 2, 3, 1)                                    # what the reference wrappers pass
+    gm = torch.tensor([[0.4], [0.7]])
+    out = gamma.Gamma().run(nhwc, 'manual', {'gamma': gm.cuda()})
+    assert out.shape == (2, 16, 24, 3) and maxabs(out.permute(0, 3, 1, 2), O.gamma_manual(x, gm)) <= 1e-4
+    gain = torch.tensor([[1., 2., 0.5], [0.3, 1.2, 5.0]])
+    out = whitebalance.WhiteBalance().run(nhwc, 'manual', {'gain': gain.cuda()})
+    assert maxabs(out.permute(0, 3, 1, 2), O.wb_manual(x, gain)) <= 1e-5
+    out = whitebalance.WhiteBalance().run(nhwc, 'grayworld', {'input': {}, 'output': {}})
+    assert maxabs(out.permute(0, 3, 1, 2), O.wb_grayworld(x)) <= 1e-4
+    ratio = np.array([0.1, 0.4], dtype=np.float32)
+    out = whitebalance.WhiteBalance().run(nhwc * 255., 'whiteworld', {'white_point_ratio': ratio})
+    assert maxabs(out.permute(0, 3, 1, 2) / 255, O.wb_whiteworld(x * 255, ratio) / 255) <= 1e-4
+    wp, mg = np.array([0.6, 0.9], np.float32), np.array([0.5, 0.2], np.float32)
+    out = globaltonemapping.GlobalToneMapping().run(nhwc * 255., 'reinhard', {'white_point': wp, 'middle_grey': mg})
+    assert maxabs(out.permute(0, 3, 1, 2) / 255, O.tone_reinhard(x * 255, T(wp), T(mg)) / 255) <= 1e-4
+    out = globaltonemapping.GlobalToneMapping().run(nhwc * 255., 'filmic', {'white_point': wp, 'exposure_bias': mg * 9 + 1})
+    assert maxabs(out.permute(0, 3, 1, 2) / 255, O.tone_filmic(x * 255, T(wp), T(mg * 9 + 1)) / 255) <= 1e-4
+    out = globaltonemapping.GlobalToneMapping().run(nhwc * 255., 'crysisengine', {'lum_adapted': mg})
+    assert maxabs(out.permute(0, 3, 1, 2) / 255, O.tone_crysis(x * 255, T(mg)) / 255) <= 1e-4
+    raw = torch.rand(2, 1, 16, 24, generator=g)
+    desc = {'input': {'format': 'RGGB', 'bitdepth': 10}, 'output': {'format': 'BGR', 'bitdepth': 8}}
+    out = demosaic.Demosaic().run(raw.cuda(), 'nearestneighbor', desc)
+    assert out.shape == (2, 3, 16, 24) and torch.equal(out.cpu(), O.demosaic_nearest(raw))
+    out = demosaic.Demosaic().run((raw.cuda() * 255).permute(0, 2, 3, 1), 'laplacian', desc)
+    assert out.shape == (2, 16, 24, 3) and maxabs(out.permute(0, 3, 1, 2) / 255, O.demosaic_laplacian(raw * 255, 255.) / 255) <= 1e-5
+    out = spatialnoisereduction.SpatialNoiseReduction().run(nhwc * 255., 'median', {'size': 5})
+    assert torch.equal(out.permute(0, 3, 1, 2).cpu(), O.denoise_median(x * 255, 5))
+    win = torch.tensor([3, 3], dtype=torch.int32)
+    out = spatialnoisereduction.SpatialNoiseReduction().run(nhwc * 255., 'bilateral', {
+        'window_length': win.cuda(), 'sigma_color': torch.tensor([20., 50.]).cuda(), 'sigma_space': torch.tensor([5., 2.]).cuda()})
+    assert maxabs(out.permute(0, 3, 1, 2) / 255, O.denoise_bilateral(x * 255, win, [20., 50.], [5., 2.]) / 255) <= 1e-4
+    with pytest.raises(ValueError):
+        gamma.Gamma().run(nhwc, 'auto', {})
