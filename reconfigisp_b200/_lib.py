@@ -12,7 +12,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(HERE), 'include', 'reconfigisp_b200.h')
-LIB_PATH = os.path.join(HERE, 'libreconfigisp_b200.so')
+LIB_PATH = os.environ.get('RISP_LIB_PATH', os.path.join(HERE, 'libreconfigisp_b200.so'))
 
 RISP_OK, RISP_E_INVALID, RISP_E_ALIGN, RISP_E_CUDA, RISP_E_UNSUPPORTED, RISP_E_WORKSPACE = 0, -1, -2, -3, -4, -5
 

@@ -182,7 +182,7 @@ mixed_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, floa
         for (int k = 0; k < NPX; ++k) a = fmaf(G.b[k], t.b[k], fmaf(G.g[k], t.g[k], fmaf(G.r[k], t.r[k], a)));
         dot[j] += a;
         Px<NPX> dd = G;
-        stage_bwd<NPX, BIG>(d.op[j], d.iarg[j], prow + d.off[j], X, dd, accS[j], accB);
+        stage_bwd<NPX, BIG>(d.op[j], d.iarg[j], prow + d.off[j], X, t, dd, accS[j], accB);
 #pragma unroll
         for (int k = 0; k < NPX; ++k) {
           DX.b[k] = fmaf(wk[j], dd.b[k], DX.b[k]); DX.g[k] = fmaf(wk[j], dd.g[k], DX.g[k]); DX.r[k] = fmaf(wk[j], dd.r[k], DX.r[k]);

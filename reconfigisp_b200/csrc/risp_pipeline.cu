@@ -130,8 +130,15 @@ struct PipeArgs {
   int gt_is_dy;       // MODE_STEP: `gt` holds dL/dy (container-level backward) instead of the target
 };
 
+#ifndef RISP_STEP_MINB
+#define RISP_STEP_MINB 2   // resident CTAs per SM the backward-carrying kernels are compiled for (register cap)
+#endif
+#ifndef RISP_FWD_MINB
+#define RISP_FWD_MINB 4
+#endif
+
 template <int DM, int MODE, unsigned SIG, bool BIGG>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, (MODE == 1 /*MODE_STEP*/) ? ((SIG == 0) ? 1 : RISP_STEP_MINB) : RISP_FWD_MINB)
 pipeline_kernel(PipeArgs a, ChainDesc d) {
   using SG = Sig<SIG>;
   constexpr int SMAX = SG::S;
@@ -148,7 +155,8 @@ pipeline_kernel(PipeArgs a, ChainDesc d) {
   const int rb = min(H, ra + a.rows_per_chunk);
   const long long plane = (long long)H * W;
   const float* __restrict__ img = a.raw + (long long)n * plane;
-  const float* __restrict__ prow = a.params + (long long)n * a.pstride;
+  const float* __restrict__ prow_inv = a.params + (long long)n * a.pstride;
+  const float* __restrict__ prow = prow_inv;
   const float* __restrict__ gtb = (MODE == MODE_STEP) ? a.gt + (long long)n * 3 * plane : nullptr;
   float* __restrict__ yb = a.y ? a.y + (long long)n * 3 * plane : nullptr;
 
@@ -195,32 +203,57 @@ pipeline_kernel(PipeArgs a, ChainDesc d) {
         for (int s = 0; s < SMAX; ++s)
           if (SG::live(d, s)) stage_fwd(SG::op(d, s), SG::iarg(d, s), prow + d.off[s], px);
       } else {
-        Px<4> saved[SMAX];
-#pragma unroll
-        for (int s = 0; s < SMAX; ++s) {
-          if (SG::live(d, s)) {
-            saved[s] = px;
-            stage_fwd(SG::op(d, s), SG::iarg(d, s), prow + d.off[s], px);
-          }
-        }
+        // Backward-carrying mode: the 4 pixels of the lane are processed as two sequential PAIRS so that
+        // only one pair's saved activations / gradients are live at a time (register pressure decides the
+        // occupancy of this kernel).  The pair is selected with a warp-uniform predicate, not an index.
         const float gtB[4] = {tB.x, tB.y, tB.z, tB.w}, gtG[4] = {tG.x, tG.y, tG.z, tG.w},
                     gtR[4] = {tR.x, tR.y, tR.z, tR.w};
-        Px<4> dd;
-        if (a.gt_is_dy) {
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          const bool hi = (h != 0);
+          // Re-read the (L1-resident, warp-uniform) stage parameters in every pair iteration instead of
+          // pinning ~45 loop-invariant values in registers for the whole kernel: the opaque asm hides the
+          // invariance from the compiler.
+          const float* prow = prow_inv;
+          asm volatile("" : "+l"(prow));
+          Px<2> saved[SMAX + 1];        // saved[s] = input of stage s, saved[s+1] = its output
+          Px<2> cur, tgt;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) { dd.b[k] = gtB[k]; dd.g[k] = gtG[k]; dd.r[k] = gtR[k]; }
-        } else {
-          // d loss / d y up to the constant 2/numel, applied by the finaliser
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            dd.b[k] = active ? px.b[k] - gtB[k] : 0.f; dd.g[k] = active ? px.g[k] - gtG[k] : 0.f;
-            dd.r[k] = active ? px.r[k] - gtR[k] : 0.f;
-            loss = fmaf(dd.b[k], dd.b[k], fmaf(dd.g[k], dd.g[k], fmaf(dd.r[k], dd.r[k], loss)));
+          for (int k = 0; k < 2; ++k) {
+            cur.b[k] = hi ? px.b[2 + k] : px.b[k]; cur.g[k] = hi ? px.g[2 + k] : px.g[k]; cur.r[k] = hi ? px.r[2 + k] : px.r[k];
+            tgt.b[k] = hi ? gtB[2 + k] : gtB[k]; tgt.g[k] = hi ? gtG[2 + k] : gtG[k]; tgt.r[k] = hi ? gtR[2 + k] : gtR[k];
           }
-        }
+          saved[0] = cur;
 #pragma unroll
-        for (int s = SMAX - 1; s >= 0; --s)
-          if (SG::live(d, s)) stage_bwd<4, BIG>(SG::op(d, s), SG::iarg(d, s), prow + d.off[s], saved[s], dd, accS[s], accB);
+          for (int s = 0; s < SMAX; ++s) {
+            if (SG::live(d, s)) {
+              stage_fwd(SG::op(d, s), SG::iarg(d, s), prow + d.off[s], cur);
+              saved[s + 1] = cur;
+            }
+          }
+          if (yb) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              if (hi) { px.b[2 + k] = cur.b[k]; px.g[2 + k] = cur.g[k]; px.r[2 + k] = cur.r[k]; }
+              else { px.b[k] = cur.b[k]; px.g[k] = cur.g[k]; px.r[k] = cur.r[k]; }
+            }
+          }
+          Px<2> dd;
+          if (a.gt_is_dy) {
+            dd = tgt;
+          } else {
+            // d loss / d y up to the constant 2/numel, applied by the finaliser
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              dd.b[k] = active ? cur.b[k] - tgt.b[k] : 0.f; dd.g[k] = active ? cur.g[k] - tgt.g[k] : 0.f;
+              dd.r[k] = active ? cur.r[k] - tgt.r[k] : 0.f;
+              loss = fmaf(dd.b[k], dd.b[k], fmaf(dd.g[k], dd.g[k], fmaf(dd.r[k], dd.r[k], loss)));
+            }
+          }
+#pragma unroll
+          for (int s = SMAX - 1; s >= 0; --s)
+            if (SG::live(d, s)) stage_bwd<2, BIG>(SG::op(d, s), SG::iarg(d, s), prow + d.off[s], saved[s], saved[s + 1], dd, accS[s], accB);
+        }
       }
       if (yb && active) {
         const long long o = (long long)r * W + c0;

@@ -161,18 +161,19 @@ chain_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, floa
     X.load(xb, HW, i, stride, nvec, 1.f);
     D.load(gb, HW, i, stride, nvec, 1.f);      // out-of-range tail pixels get d = 0
     constexpr int NPX = Group<VEC, 1>::NPX;
-    Px<NPX> saved[SMAX];
+    Px<NPX> saved[SMAX + 1];        // saved[s] = input of stage s, saved[s+1] = its output
+    saved[0] = X.px;
 #pragma unroll
     for (int s = 0; s < SMAX; ++s) {
       if (SG::live(d, s)) {
-        saved[s] = X.px;
-        if (SG::generic ? (s + 1 < d.S) : (s + 1 < SMAX)) stage_fwd(SG::op(d, s), SG::iarg(d, s), prow + d.off[s], X.px);
+        stage_fwd(SG::op(d, s), SG::iarg(d, s), prow + d.off[s], X.px);
+        saved[s + 1] = X.px;
       }
     }
 #pragma unroll
     for (int s = SMAX - 1; s >= 0; --s)
       if (SG::live(d, s))
-        stage_bwd<NPX, BIG>(SG::op(d, s), SG::iarg(d, s), prow + d.off[s], saved[s], D.px, accS[s], accB);
+        stage_bwd<NPX, BIG>(SG::op(d, s), SG::iarg(d, s), prow + d.off[s], saved[s], saved[s + 1], D.px, accS[s], accB);
     if (ob) D.store(ob, HW, i, stride, nvec, 1.f);
   }
   flush_accumulators<BIG, SMAX>(accS, accB, 0.f, partial + ((long long)n * gridDim.x + blockIdx.x) * RISP_NSLOT,

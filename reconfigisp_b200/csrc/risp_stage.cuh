@@ -55,21 +55,24 @@ __device__ __forceinline__ float gamma_px(float x, float gm) {
 // which needs no segment search.  Pixels outside [0,1) pass through and are clamped (:438), i.e. 0 / 1.
 struct GtmCoef {
   float s0;
-  float ds[4];   // slope increments at x_1..x_4 (unused entries are 0)
+  float ds[4];   // slope increments at the interior knots x_1..x_{n-1} (unused entries are 0)
   float xk[4];
   float fn;
+  bool knots_in_range;   // all y_k in [0,1]  =>  f(x) in [0,1] on [0,1) and the clamp mask is always 1
 };
 
 __device__ __forceinline__ GtmCoef gtm_prepare(const float* __restrict__ p, int n) {
   GtmCoef c;
   const float fn = (float)n;
   c.fn = fn;
+  c.knots_in_range = true;
   float prev_y = 0.f, prev_s = 0.f;
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
     float s = 0.f;
     if (k < n) {
       const float ey = (k < n - 1) ? p[k] : 1.f;
+      if (k < n - 1) c.knots_in_range = c.knots_in_range && (ey >= 0.f) && (ey <= 1.f);
       s = (ey - prev_y) * fn;
       prev_y = ey;
     }
@@ -80,11 +83,12 @@ __device__ __forceinline__ GtmCoef gtm_prepare(const float* __restrict__ p, int 
   return c;
 }
 
-__device__ __forceinline__ float gtm_px(float x, const GtmCoef& c) {
+__device__ __forceinline__ float gtm_px(float x, const GtmCoef& c, int n) {
   const float xc = fminf(fmaxf(x, 0.f), 1.f);
   float f = c.s0 * xc;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) f = fmaf(c.ds[k], fmaxf(xc - c.xk[k], 0.f), f);
+  for (int k = 0; k < 4; ++k)
+    if (k < n - 1) f = fmaf(c.ds[k], fmaxf(xc - c.xk[k], 0.f), f);
   return fminf(fmaxf(f, 0.f), 1.f);
 }
 
@@ -93,17 +97,18 @@ __device__ __forceinline__ float gtm_px(float x, const GtmCoef& c) {
 __device__ __forceinline__ void gtm_bwd_px(float x, const GtmCoef& c, int n, float& d,
                                            float (&accS)[RISP_SMALL_ACC]) {
   const bool inside = (x >= 0.f) && (x < 1.f);
-  float slope = c.s0, f = c.s0 * x;
+  float slope = c.s0;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float h = x - c.xk[k];
-    const bool on = (h >= 0.f);
-    slope += on ? c.ds[k] : 0.f;
-    f = fmaf(c.ds[k], fmaxf(h, 0.f), f);
+  for (int k = 0; k < 4; ++k)
+    if (k < n - 1) slope += (x >= c.xk[k]) ? c.ds[k] : 0.f;
+  float dm = inside ? d : 0.f;
+  if (!c.knots_in_range) {           // block-uniform, never taken for sigmoid-generated knots
+    float f = c.s0 * x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < n - 1) f = fmaf(c.ds[k], fmaxf(x - c.xk[k], 0.f), f);
+    dm = (f >= 0.f && f <= 1.f) ? dm : 0.f;
   }
-  // pass-through region: out = x, clamp mask inclusive -> only x == 1 keeps a gradient (slope 1)
-  const float m_in = (f >= 0.f && f <= 1.f) ? 1.f : 0.f;
-  const float dm = inside ? d * m_in : 0.f;
 #pragma unroll
   for (int j = 0; j < RISP_SMALL_ACC; ++j) {
     if (j < n - 1) {
@@ -111,6 +116,7 @@ __device__ __forceinline__ void gtm_bwd_px(float x, const GtmCoef& c, int n, flo
       accS[j] = fmaf(dm, hat, accS[j]);
     }
   }
+  // pass-through region: out = x, clamp mask inclusive -> only x == 1 keeps a gradient (slope 1)
   d = inside ? dm * slope : ((x == 1.f) ? d : 0.f);
 }
 
@@ -174,7 +180,7 @@ __device__ __forceinline__ void stage_fwd(int op, int iarg, const float* __restr
     case RISP_OP_GTM: {
       const GtmCoef c = gtm_prepare(p, iarg);
 #pragma unroll
-      for (int k = 0; k < NPX; ++k) { x.b[k] = gtm_px(x.b[k], c); x.g[k] = gtm_px(x.g[k], c); x.r[k] = gtm_px(x.r[k], c); }
+      for (int k = 0; k < NPX; ++k) { x.b[k] = gtm_px(x.b[k], c, iarg); x.g[k] = gtm_px(x.g[k], c, iarg); x.r[k] = gtm_px(x.r[k], c, iarg); }
     } break;
     case RISP_OP_CCM: {
       float q[9];
@@ -216,24 +222,25 @@ __device__ __forceinline__ void stage_fwd(int op, int iarg, const float* __restr
 // accS: this stage's small accumulators; accB: the chain's big accumulator, 30 floats viewed as 15
 // float2 (POLY10 coefficient pairs (P[c][2j], P[c][2j+1]) -> one FFMA2 per pair).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void gamma_bwd_px(float x, float gm, float& d, float& dgm) {
+__device__ __forceinline__ void gamma_bwd_px(float x, float y, float gm, float& d, float& dgm) {
   const float xc = fminf(fmaxf(x, RISP_GAMMA_EPS), 1.f);
   const float l2 = lg2_ftz(xc);
-  const float y = ex2_ftz(gm * l2);
   dgm = fmaf(d * y, l2, dgm);                         // * ln2 applied once when the accumulator is flushed
   const bool inside = (x >= RISP_GAMMA_EPS) && (x <= 1.f);
   d = inside ? d * gm * y * rcp_ftz(xc) : 0.f;
 }
 
+// y = the stage's OUTPUT (already computed by the forward sweep; saves recomputing it here)
 template <int NPX, bool BIG>
-__device__ __forceinline__ void stage_bwd(int op, int iarg, const float* __restrict__ p, const Px<NPX>& x, Px<NPX>& d,
-                                          float (&accS)[RISP_SMALL_ACC], float2 (&accB)[RISP_BIG_ACC]) {
+__device__ __forceinline__ void stage_bwd(int op, int iarg, const float* __restrict__ p, const Px<NPX>& x,
+                                          const Px<NPX>& y, Px<NPX>& d, float (&accS)[RISP_SMALL_ACC],
+                                          float2 (&accB)[RISP_BIG_ACC]) {
   switch (op) {
     case RISP_OP_GAMMA: {
       const float gm = p[0];
       float a = 0.f;
 #pragma unroll
-      for (int k = 0; k < NPX; ++k) { gamma_bwd_px(x.b[k], gm, d.b[k], a); gamma_bwd_px(x.g[k], gm, d.g[k], a); gamma_bwd_px(x.r[k], gm, d.r[k], a); }
+      for (int k = 0; k < NPX; ++k) { gamma_bwd_px(x.b[k], y.b[k], gm, d.b[k], a); gamma_bwd_px(x.g[k], y.g[k], gm, d.g[k], a); gamma_bwd_px(x.r[k], y.r[k], gm, d.r[k], a); }
       accS[0] = fmaf(a, RISP_LN2, accS[0]);
     } break;
     case RISP_OP_GAIN: {
@@ -248,7 +255,9 @@ __device__ __forceinline__ void stage_bwd(int op, int iarg, const float* __restr
       const float g0 = p[0], g1 = p[1], g2 = p[2];
 #pragma unroll
       for (int k = 0; k < NPX; ++k) {
-        const float e0 = d.b[k] * in01(x.b[k] * g0), e1 = d.g[k] * in01(x.g[k] * g1), e2 = d.r[k] * in01(x.r[k] * g2);
+        const float u0 = x.b[k] * g0, u1 = x.g[k] * g1, u2 = x.r[k] * g2;
+        const float e0 = (u0 >= 0.f && u0 <= 1.f) ? d.b[k] : 0.f, e1 = (u1 >= 0.f && u1 <= 1.f) ? d.g[k] : 0.f,
+                    e2 = (u2 >= 0.f && u2 <= 1.f) ? d.r[k] : 0.f;
         accS[0] = fmaf(e0, x.b[k], accS[0]); accS[1] = fmaf(e1, x.g[k], accS[1]); accS[2] = fmaf(e2, x.r[k], accS[2]);
         d.b[k] = e0 * g0; d.g[k] = e1 * g1; d.r[k] = e2 * g2;
       }
@@ -272,7 +281,8 @@ __device__ __forceinline__ void stage_bwd(int op, int iarg, const float* __restr
             float2 u = __fmul2_rn(q2[c * 5 + 4], phi[4]);
 #pragma unroll
             for (int i = 3; i >= 0; --i) u = __ffma2_rn(q2[c * 5 + i], phi[i], u);
-            const float2 e = splat(din[c] * in01(u.x + u.y));
+            const float us = u.x + u.y;
+            const float2 e = splat((us >= 0.f && us <= 1.f) ? din[c] : 0.f);
 #pragma unroll
             for (int i = 0; i < 5; ++i) {
               dphi[i] = __ffma2_rn(e, q2[c * 5 + i], dphi[i]);
