@@ -233,6 +233,24 @@ int risp_whole2patch(const float* frame, float* tiles, int C, int H, int W, int 
 int risp_patch2whole(const float* tiles, float* frame, int C, int H, int W, int h, int w, int sh, int sw,
                      const int* ys, int ny, const int* xs, int nx, int clip01, risp_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Dense convolution for the CNN candidates (srcnn_res_arch.py:15-24, srcnn_demosaic_arch.py:14-25,
+ * path_14l_bayer_arch.py:6-57, path_14l_bgr_arch.py): NCHW fp32, stride 1, "same" zero padding,
+ * K in {1,3,5,9}, exact fp32 accumulation, with the fusions those architectures need.
+ *   y = [mask_out > 0] * ( act_out( conv(act_in([mask_in > 0] * x), W) + bias ) + res' )
+ * flags: RELU_IN (the leading in-place ReLU of ResidualBlock, path_14l_bayer_arch.py:9-21), RELU_OUT,
+ * ADD_RES, RES_RELU (res' = relu(res): the relu-skip quirk).  The masks serve the backward pass.
+ * Weights are passed in the prepared layout (Cin, K*K, CoutPad); transpose_flip != 0 prepares the
+ * operator of the data gradient (dx = conv(dy, W^T flipped)) from the same nn.Conv2d weight.
+ * ------------------------------------------------------------------------------------- */
+enum risp_conv_flags { RISP_CONV_RELU_IN = 1, RISP_CONV_RELU_OUT = 2, RISP_CONV_ADD_RES = 4, RISP_CONV_RES_RELU = 8 };
+size_t risp_conv2d_prepared_weight_floats(int Cin, int Cout, int K, int transpose_flip);
+int risp_conv2d_prepare_weights(const float* weight, float* wk, int Cin, int Cout, int K, int transpose_flip,
+                                risp_stream_t stream);
+int risp_conv2d_fwd(const float* x, const float* mask_in, const float* wk, const float* bias, const float* res,
+                    const float* mask_out, float* y, int N, int Cin, int Cout, int H, int W, int K, int flags,
+                    risp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -591,3 +591,76 @@ def patch2whole(tiles, frame_hw, stride, clip01=False):
     L.call('risp_patch2whole', L.ptr(tiles), L.ptr(out), C, H, W, h, w, sh, sw, L.iarr(ys), len(ys), L.iarr(xs), len(xs),
            int(bool(clip01)), L.stream())
     return out
+
+
+# ---- dense convolution of the CNN candidates -------------------------------------------------------------
+CONV_RELU_IN, CONV_RELU_OUT, CONV_ADD_RES, CONV_RES_RELU = (L.ENUMS['RISP_CONV_RELU_IN'], L.ENUMS['RISP_CONV_RELU_OUT'],
+                                                           L.ENUMS['RISP_CONV_ADD_RES'], L.ENUMS['RISP_CONV_RES_RELU'])
+def _prepared_weights(weight, transpose_flip):
+    """(Cout,Cin,K,K) -> kernel layout.  Cached ON the weight tensor object (so the cache dies with it; a
+    pointer-keyed cache would alias once the allocator reuses the address) and keyed by its version counter."""
+    cache = getattr(weight, '_risp_wk', None)
+    key = (bool(transpose_flip), weight._version, weight.data_ptr())
+    if cache is None or key not in cache:
+        Cout, Cin, K, _ = weight.shape
+        n = L.size('risp_conv2d_prepared_weight_floats', Cin, Cout, K, int(transpose_flip))
+        wk = torch.empty((n,), device=weight.device, dtype=torch.float32)
+        L.call('risp_conv2d_prepare_weights', L.ptr(weight.detach().contiguous()), L.ptr(wk), Cin, Cout, K, int(transpose_flip), L.stream())
+        if cache is None or len(cache) > 8:
+            cache = {}
+        cache[key] = wk
+        try:
+            weight._risp_wk = cache
+        except Exception:
+            pass
+    return cache[key]
+
+
+def _conv_raw(x, mask_in, wk, bias, res, mask_out, Cout, K, flags):
+    N, Cin, H, W = x.shape
+    y = torch.empty((N, Cout, H, W), device=x.device, dtype=torch.float32)
+    L.call('risp_conv2d_fwd', L.ptr(x), L.ptr(mask_in), L.ptr(wk), L.ptr(bias), L.ptr(res), L.ptr(mask_out), L.ptr(y),
+           N, Cin, Cout, H, W, K, int(flags), L.stream())
+    return y
+
+
+class _ConvFn(torch.autograd.Function):
+    """y = relu_out?(conv(relu_in?(x), W) + b) + relu?(res).  Backward: data gradients only -- the candidate
+    networks are frozen constants on this path."""
+
+    @staticmethod
+    def forward(ctx, x, res, weight, bias, relu_in, relu_out, res_relu):
+        x = _img(x)
+        Cout, Cin, K, _ = weight.shape
+        assert x.shape[1] == Cin, 'conv2d: %d input channels, weight expects %d' % (x.shape[1], Cin)
+        assert not (relu_out and res is not None), 'output ReLU and residual never co-occur in the candidate nets'
+        flags = (CONV_RELU_IN if relu_in else 0) | (CONV_RELU_OUT if relu_out else 0)
+        if res is not None:
+            res = _img(res, Cout)
+            flags |= CONV_ADD_RES | (CONV_RES_RELU if res_relu else 0)
+        b = None if bias is None else bias.detach().float().contiguous()
+        y = _conv_raw(x, None, _prepared_weights(weight, False), b, res, None, Cout, K, flags)
+        ctx.cfg = (relu_in, relu_out, res_relu, Cin, K)
+        ctx.save_for_backward(x if relu_in else None, y if relu_out else None, res if (res is not None and res_relu) else None, weight)
+        ctx.has_res = res is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, res, weight = ctx.saved_tensors
+        relu_in, relu_out, res_relu, Cin, K = ctx.cfg
+        dy = dy.contiguous()
+        dx = dres = None
+        if ctx.needs_input_grad[0]:
+            # dx = [x > 0]? * conv(dy * [y > 0]?, W^T flipped)
+            dx = _conv_raw(dy, y if relu_out else None, _prepared_weights(weight, True), None, None, x if relu_in else None,
+                           Cin, K, 0)
+        if ctx.has_res and ctx.needs_input_grad[1]:
+            dres = dy if not res_relu else dy * (res > 0).to(dy.dtype)
+        if weight.requires_grad and ctx.needs_input_grad[2]:
+            raise NotImplementedError('weight gradients of the candidate nets (proxy fine-tuning, SURVEY §8f) are not built yet')
+        return dx, dres, None, None, None, None, None
+
+
+def conv2d(x, weight, bias=None, relu_in=False, relu_out=False, residual=None, residual_relu=False):
+    return _ConvFn.apply(x, residual, weight, bias, relu_in, relu_out, residual_relu)

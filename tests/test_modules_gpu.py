@@ -35,7 +35,7 @@ def test_cnn_candidates_match_reference(golden):
     torch.backends.cuda.matmul.allow_tf32 = False
     for name, net, seed in specs:
         net.load_state_dict(P.seeded_state_dict(net, seed))
-        net = net.cuda()
+        net = net.cuda().requires_grad_(False)        # candidate nets are frozen constants on this path
         if name.startswith('srcnn_res'):
             y = net(x3, T(g[name + '_par']).cuda()); inp = x3
         elif name == 'path14l_bgr':

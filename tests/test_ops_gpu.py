@@ -403,3 +403,32 @@ def test_errors_map_to_reference_exceptions(ops):
         ops.demosaic(r, 'bilinear').sum().backward()
     with pytest.raises(ValueError):
         ops.demosaic(torch.rand(1, 1, 8, 6).cuda(), 'bilinear')      # W % 4 != 0
+
+
+@pytest.mark.parametrize('cfg', [(3, 64, 64, 3), (2, 15, 64, 9), (2, 64, 32, 5), (2, 32, 3, 5), (2, 64, 32, 1), (1, 4, 64, 3), (2, 64, 4, 3), (1, 32, 12, 5)])
+def test_conv2d_fwd_and_data_gradient(ops, cfg):
+    """The dense convolution of the CNN candidates against torch's fp64 convolution on the CPU."""
+    import torch.nn.functional as F
+    N, Cin, Cout, K = cfg
+    H, W = 23, 40
+    g = torch.Generator().manual_seed(31 + K + Cin)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, K, K, generator=g) * (1.0 / (K * Cin ** 0.5))
+    b = torch.randn(Cout, generator=g) * 0.1
+    res = torch.randn(N, Cout, H, W, generator=g)
+    d = torch.randn(N, Cout, H, W, generator=g)
+    for relu_in, relu_out, use_res, res_relu in ((False, False, False, False), (True, True, False, False), (False, False, True, True),
+                                                 (True, False, True, False)):
+        xo, ro = x.double().requires_grad_(), res.double().requires_grad_()
+        yo = F.conv2d(torch.relu(xo) if relu_in else xo, w.double(), b.double(), padding=K // 2)
+        if relu_out:
+            yo = torch.relu(yo)
+        if use_res:
+            yo = yo + (torch.relu(ro) if res_relu else ro)
+        go = torch.autograd.grad(yo, (xo, ro) if use_res else (xo,), d.double())
+        xg, rg = dev(x).requires_grad_(), dev(res).requires_grad_()
+        yg = ops.conv2d(xg, dev(w), dev(b), relu_in, relu_out, rg if use_res else None, res_relu)
+        gg = torch.autograd.grad(yg, (xg, rg) if use_res else (xg,), dev(d))
+        assert maxabs(yg, yo) <= 2e-5, (cfg, relu_in, relu_out, use_res)
+        for a, bb in zip(gg, go):
+            assert maxabs(a, bb) <= 5e-5, (cfg, relu_in, relu_out, use_res)
