@@ -133,6 +133,9 @@ struct PipeArgs {
 #ifndef RISP_STEP_MINB
 #define RISP_STEP_MINB 2   // resident CTAs per SM the backward-carrying kernels are compiled for (register cap)
 #endif
+#ifndef RISP_PAIR_UNROLL
+#define RISP_PAIR_UNROLL 2
+#endif
 #ifndef RISP_FWD_MINB
 #define RISP_FWD_MINB 4
 #endif
@@ -208,14 +211,10 @@ pipeline_kernel(PipeArgs a, ChainDesc d) {
         // occupancy of this kernel).  The pair is selected with a warp-uniform predicate, not an index.
         const float gtB[4] = {tB.x, tB.y, tB.z, tB.w}, gtG[4] = {tG.x, tG.y, tG.z, tG.w},
                     gtR[4] = {tR.x, tR.y, tR.z, tR.w};
-#pragma unroll 1
+constexpr int kPairUnroll = RISP_PAIR_UNROLL;
+#pragma unroll kPairUnroll
         for (int h = 0; h < 2; ++h) {
           const bool hi = (h != 0);
-          // Re-read the (L1-resident, warp-uniform) stage parameters in every pair iteration instead of
-          // pinning ~45 loop-invariant values in registers for the whole kernel: the opaque asm hides the
-          // invariance from the compiler.
-          const float* prow = prow_inv;
-          asm volatile("" : "+l"(prow));
           Px<2> saved[SMAX + 1];        // saved[s] = input of stage s, saved[s+1] = its output
           Px<2> cur, tgt;
 #pragma unroll

@@ -94,6 +94,7 @@ __device__ __forceinline__ float gtm_px(float x, const GtmCoef& c, int n) {
 
 // backward: d (in: dL/dout, out: dL/dx) and the knot gradients via the hat basis
 //   d out / d y_j = max(0, 1 - n |x - x_j|)  for x in [0,1)
+template <bool CHECK_RANGE>
 __device__ __forceinline__ void gtm_bwd_px(float x, const GtmCoef& c, int n, float& d,
                                            float (&accS)[RISP_SMALL_ACC]) {
   const bool inside = (x >= 0.f) && (x < 1.f);
@@ -102,7 +103,7 @@ __device__ __forceinline__ void gtm_bwd_px(float x, const GtmCoef& c, int n, flo
   for (int k = 0; k < 4; ++k)
     if (k < n - 1) slope += (x >= c.xk[k]) ? c.ds[k] : 0.f;
   float dm = inside ? d : 0.f;
-  if (!c.knots_in_range) {           // block-uniform, never taken for sigmoid-generated knots
+  if (CHECK_RANGE) {                 // only when some knot lies outside [0,1] (never for sigmoid-generated knots)
     float f = c.s0 * x;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
@@ -298,10 +299,18 @@ __device__ __forceinline__ void stage_bwd(int op, int iarg, const float* __restr
       break;
     case RISP_OP_GTM: {
       const GtmCoef c = gtm_prepare(p, iarg);
+      if (c.knots_in_range) {      // block-uniform
 #pragma unroll
-      for (int k = 0; k < NPX; ++k) {
-        gtm_bwd_px(x.b[k], c, iarg, d.b[k], accS); gtm_bwd_px(x.g[k], c, iarg, d.g[k], accS);
-        gtm_bwd_px(x.r[k], c, iarg, d.r[k], accS);
+        for (int k = 0; k < NPX; ++k) {
+          gtm_bwd_px<false>(x.b[k], c, iarg, d.b[k], accS); gtm_bwd_px<false>(x.g[k], c, iarg, d.g[k], accS);
+          gtm_bwd_px<false>(x.r[k], c, iarg, d.r[k], accS);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < NPX; ++k) {
+          gtm_bwd_px<true>(x.b[k], c, iarg, d.b[k], accS); gtm_bwd_px<true>(x.g[k], c, iarg, d.g[k], accS);
+          gtm_bwd_px<true>(x.r[k], c, iarg, d.r[k], accS);
+        }
       }
     } break;
     case RISP_OP_CCM:
