@@ -113,6 +113,12 @@ int risp_bayer_blc_wb_bwd(const float* raw, const float* dout, float* draw, floa
                           int W, const float* params, int param_stride, void* workspace,
                           size_t workspace_bytes, risp_stream_t stream);
 
+/* Device-side input codec: unsigned 8/16-bit codes -> fp32 code/denom, exactly the
+ * host-side normalisation of the reference loaders (x/1023. s7isp_rggb2bgr_dataset.py:123, x/16383.
+ * sid_sony_ratio_rggb2bgr_dataset.py:133, gt/255. :134) but after the PCIe hop (5 instead of 16 B/px). */
+int risp_decode_codes(const void* src, float* dst, long long n, int bytes_per_code, float denom,
+                      risp_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * Fused fixed pipeline (isp_universal.py:210-232 / origin_universal.py:143-161 as ONE pass):
  *   raw --[blc/wb]--> demosaic(kind) --> per-pixel chain --> y        (16 B/px algorithmic)

@@ -259,3 +259,44 @@ extern "C" int risp_bayer_blc_wb_bwd(const float* raw, const float* dout, float*
   }
   return finalize_partials(partial, dparams, N, B, 8, P, idx, idx, 5, 1.f, param_stride == 0, st);
 }
+
+// ---- device-side input codec: integer sensor / display codes -> fp32 in [0,1] ---------------------------
+// The reference's loaders decode 16-bit PNG Bayer frames and 8-bit ground truth on the HOST and ship fp32
+// (x/1023. s7isp_rggb2bgr_dataset.py:123, x/16383. sid_sony_ratio_rggb2bgr_dataset.py:133, gt/255. :134),
+// i.e. 16 B/px over PCIe.  Shipping the codes (2 + 3 B/px) and normalising here cuts the host->device
+// volume 3.2x; the arithmetic is the same single fp32 multiply... the loaders use a DIVISION, so this does too.
+namespace risp {
+template <typename T>
+__global__ void __launch_bounds__(256)
+decode_kernel(const T* __restrict__ src, float* __restrict__ dst, long long n, float denom) {
+  const long long nv = n / 4;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < nv; i += (long long)gridDim.x * 256) {
+    float v[4];
+    if (sizeof(T) == 2) {
+      const uint2 t = *reinterpret_cast<const uint2*>(src + 4 * i);
+      v[0] = (float)(t.x & 0xffffu); v[1] = (float)(t.x >> 16); v[2] = (float)(t.y & 0xffffu); v[3] = (float)(t.y >> 16);
+    } else {
+      const unsigned t = *reinterpret_cast<const unsigned*>(src + 4 * i);
+      v[0] = (float)(t & 0xffu); v[1] = (float)((t >> 8) & 0xffu); v[2] = (float)((t >> 16) & 0xffu); v[3] = (float)(t >> 24);
+    }
+    st_stream4(dst + 4 * i, make_float4(__fdiv_rn(v[0], denom), __fdiv_rn(v[1], denom), __fdiv_rn(v[2], denom), __fdiv_rn(v[3], denom)));
+  }
+  for (long long i = nv * 4 + (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+    dst[i] = __fdiv_rn((float)src[i], denom);
+}
+}  // namespace risp
+
+extern "C" int risp_decode_codes(const void* src, float* dst, long long n, int bytes_per_code, float denom,
+                                 risp_stream_t stream) {
+  RISP_REQUIRE(src && dst && n > 0 && denom > 0.f, RISP_E_INVALID, "risp_decode_codes: bad arguments");
+  RISP_REQUIRE(bytes_per_code == 1 || bytes_per_code == 2, RISP_E_INVALID, "risp_decode_codes: 1 or 2 bytes per code");
+  RISP_REQUIRE((reinterpret_cast<uintptr_t>(src) & 7) == 0 && aligned16(dst), RISP_E_ALIGN, "risp_decode_codes: alignment");
+  long long g = cdiv(n / 4 + 1, 256);
+  long long cap = (long long)sm_count() * 16;
+  int grid = (int)(g > cap ? cap : g);
+  if (bytes_per_code == 2)
+    decode_kernel<unsigned short><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const unsigned short*>(src), dst, n, denom);
+  else
+    decode_kernel<unsigned char><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const unsigned char*>(src), dst, n, denom);
+  return check_launch("decode_kernel");
+}

@@ -337,6 +337,18 @@ def bayer_blc_wb(raw, params):
     return _BlcWbFn.apply(raw, params)
 
 
+def decode_codes(codes, denom):
+    """uint8 / uint16 (or int16) codes on the device -> fp32 codes/denom (the loaders' /255., /1023., /16383.)."""
+    if not codes.is_cuda:
+        raise RuntimeError('decode_codes runs on CUDA tensors only')
+    codes = codes.contiguous()
+    nbytes = codes.element_size()
+    assert nbytes in (1, 2) and not codes.dtype.is_floating_point
+    out = torch.empty(codes.shape, device=codes.device, dtype=torch.float32)
+    L.call('risp_decode_codes', L.ptr(codes), L.ptr(out), codes.numel(), nbytes, float(denom), L.stream())
+    return out
+
+
 # ---- stencils ---------------------------------------------------------------------------------------
 def bilateral(x, window, sigma_color, sigma_space, max_window=None):
     x = _img(x.detach(), 3)

@@ -50,9 +50,15 @@ class IspModel:
             self.val_gt = val_gt.to(self.device, non_blocking=True)
         else:
             raise ValueError('Invalid data format.')
-        self.img = img.to(self.device, non_blocking=True)
-        self.gt = gt.to(self.device, non_blocking=True)
+        self.img = self._to_device(img, self.opt.get('raw_white_level', 1023.))
+        self.gt = self._to_device(gt, 255.)
         self._output = None
+
+    def _to_device(self, t, denom):
+        """fp32 tensors are copied as they are (the reference's contract); integer sensor / display codes
+        (uint8, uint16/int16) are copied as codes and normalised on the device (`ops.decode_codes`)."""
+        d = t.to(self.device, non_blocking=True)
+        return d if d.dtype.is_floating_point else ops.decode_codes(d, denom)
 
     # -- training step ---------------------------------------------------------------------------------------
     def _fused_loss(self):

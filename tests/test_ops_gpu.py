@@ -432,3 +432,13 @@ def test_conv2d_fwd_and_data_gradient(ops, cfg):
         assert maxabs(yg, yo) <= 2e-5, (cfg, relu_in, relu_out, use_res)
         for a, bb in zip(gg, go):
             assert maxabs(a, bb) <= 5e-5, (cfg, relu_in, relu_out, use_res)
+
+
+def test_decode_codes_matches_loader_normalisation(ops):
+    g = torch.Generator().manual_seed(2)
+    raw = torch.randint(0, 1024, (2, 1, 17, 23), generator=g, dtype=torch.int32)
+    gt = torch.randint(0, 256, (2, 3, 17, 23), generator=g, dtype=torch.int32)
+    assert torch.equal(ops.decode_codes(raw.to(torch.int16).cuda(), 1023.).cpu(), raw.float() / 1023.)
+    assert torch.equal(ops.decode_codes(gt.to(torch.uint8).cuda(), 255.).cpu(), gt.float() / 255.)
+    big = torch.randint(0, 16384, (1, 1, 64, 128), generator=g, dtype=torch.int32)
+    assert torch.equal(ops.decode_codes(big.to(torch.int16).cuda(), 16383.).cpu(), big.float() / 16383.)
