@@ -257,6 +257,22 @@ int risp_conv2d_fwd(const float* x, const float* mask_in, const float* wk, const
                     const float* mask_out, float* y, int N, int Cin, int Cout, int H, int W, int K, int flags,
                     risp_stream_t stream);
 
+/* Tensor-core path of the same convolution: implicit GEMM on tcgen05 (kind::tf32, TMEM accumulators) with a
+ * 3-term hi/lo split so the result stays fp32-accurate (<= ~1e-6 relative), on CHANNEL-BLOCKED activations
+ * (N, H, C16/4, W, 4) where C16 = channels padded to a multiple of 16 (risp_conv_tc_padded_channels).
+ * risp_to_blocked / risp_from_blocked convert from / to planar NCHW.  Same flags and mask semantics as
+ * risp_conv2d_fwd; the output goes to the blocked tensor and/or a planar NCHW tensor (either may be NULL). */
+int risp_conv_tc_supported(int Cin, int Cout, int K);
+int risp_conv_tc_padded_channels(int C);
+size_t risp_conv_tc_weight_floats(int Cin, int Cout, int K, int transpose_flip);
+int risp_conv_tc_prepare_weights(const float* weight, float* out, int Cin, int Cout, int K, int transpose_flip,
+                                 risp_stream_t stream);
+int risp_to_blocked(const float* planar, float* blocked, int N, int C, int CG, int H, int W, risp_stream_t stream);
+int risp_from_blocked(const float* blocked, float* planar, int N, int C, int CG, int H, int W, risp_stream_t stream);
+int risp_conv_tc_fwd(const float* x_blk, const float* mask_in_blk, const float* wprep, const float* bias,
+                     const float* res_blk, const float* mask_out_blk, float* y_blk, float* y_planar, int N, int Cin,
+                     int Cout, int H, int W, int K, int flags, risp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

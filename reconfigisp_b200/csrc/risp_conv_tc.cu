@@ -1,0 +1,432 @@
+// Tensor-core convolution for the CNN candidates: implicit GEMM on tcgen05 (UMMA, kind::tf32) with TMEM
+// accumulators, fp32-accurate through a 3-term split (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo; the dropped
+// a_lo*b_lo term is ~2^-21 relative), so the 1e-4 parity bar of this path holds.
+//
+// GEMM view: M = 128 consecutive pixels of one output row, N = output channels (16..64), K = taps x input
+// channels.  Activations live in a channel-blocked layout [N][H][C/4][W][4] so that, for a group of 4 input
+// channels, the pixels of a row are a contiguous run of 16-byte elements.  Staged into shared memory as
+// [row][kgroup][pixel (tile + halo)][4] this IS the canonical no-swizzle K-major UMMA operand layout (8 x 16 B
+// core matrices, SBO = 128 B between 8-pixel groups, LBO = the kgroup stride), and a horizontal tap shift is
+// nothing but +16 B on the descriptor start address: no im2col, no data duplication across the K_w taps.
+// A CTA owns R output rows x 128 columns x all output channels: the R accumulators sit in TMEM (R*N <= 512
+// columns), every staged input row feeds up to K_h of them, and the weights of one tap row stream through
+// shared memory once per CTA and input-channel chunk.
+//
+// One elected thread issues the MMAs; completion is tracked with tcgen05.commit -> mbarrier; the epilogue
+// reads TMEM with tcgen05.ld (32x32b), applies bias / ReLU / residual and writes the blocked layout (and/or
+// planar NCHW) with 128-bit stores.
+#include "risp_common.cuh"
+
+namespace risp {
+
+constexpr int TC_M = 128;           // pixels per row tile
+constexpr int TC_THREADS = 256;
+
+struct ConvTcArgs {
+  const float* x;        // blocked (N, H, CinG, W, 4)
+  const float* wprep;    // [chunk][dy][dx][kg][CoutPad][4] hi, then the same again for lo
+  const float* bias;     // nullable (Cout)
+  const float* res;      // nullable, blocked (N, H, CoutG, W, 4)
+  const float* mask_in;  // nullable, blocked like x: x is multiplied by [mask_in > 0] while staging (backward of an output ReLU)
+  const float* mask_out; // nullable, blocked like y: the result is multiplied by [mask_out > 0] (backward of an input ReLU)
+  float* y_blk;          // nullable, blocked (N, H, CoutG, W, 4)
+  float* y_pln;          // nullable, planar (N, Cout, H, W)
+  int CinG, Cout, CoutPad, H, W, flags;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48)
+  // | layout_type SWIZZLE_NONE=0 [61,64)
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tWAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}\n"
+      ::"r"(mbar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[N]);
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- kernel ---------------------------------------------------------------------------------------------
+// K: filter size; CI_C: input channels per chunk (multiple of 8); R: output rows per CTA; NP: padded Cout (16/32/48/64)
+//
+// Accuracy note (measured on B200): every tcgen05.mma rounds its fp32 accumulator once, toward zero, so the error
+// of one accumulator grows linearly with the number of MMAs chained into it (~6e-8 relative each).  The two
+// cross terms (a_lo*b_hi, a_hi*b_lo) are ~2^-11 of the main term, so they get their OWN accumulator: the main
+// accumulator then sees one rounding per 8 input channels per tap instead of three, and the roundings of the
+// small accumulator are 2^-11 times less significant.  The two accumulators are added in the epilogue.
+template <int K, int CI_C, int R, int NP, int DYB>
+struct TcCfg {
+  static constexpr int PAD = K / 2;
+  static constexpr int PW = TC_M + K - 1;                 // staged pixels per row
+  static constexpr int KG = CI_C / 4;                     // 16-byte k-groups per chunk
+  static constexpr int ROWS = R + K - 1;
+  static constexpr int A_ROW_FLOATS = KG * PW * 4;        // one staged row, one precision
+  static constexpr int A_FLOATS = ROWS * A_ROW_FLOATS;    // hi (lo follows)
+  static constexpr int B_TAP_FLOATS = KG * NP * 4;        // one tap, one precision
+  static constexpr int B_FLOATS = DYB * K * B_TAP_FLOATS; // DYB tap rows of one chunk (hi), lo follows
+  static constexpr int B_CHUNK_FLOATS = K * K * B_TAP_FLOATS;
+  static_assert(K % DYB == 0, "tap rows per stage must divide K");
+  static constexpr size_t SMEM = sizeof(float) * (2 * A_FLOATS + 2 * B_FLOATS) + 64;
+  static constexpr int ACC_COLS = 2 * R * NP;             // main + cross-term accumulators
+  static constexpr int TMEM_COLS = (ACC_COLS <= 32) ? 32 : (ACC_COLS <= 64) ? 64 : (ACC_COLS <= 128) ? 128 : (ACC_COLS <= 256) ? 256 : 512;
+  static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
+};
+
+template <int K, int CI_C, int R, int NP, int DYB>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+conv_tc_kernel(ConvTcArgs a) {
+  using C = TcCfg<K, CI_C, R, NP, DYB>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* sA_hi = reinterpret_cast<float*>(smem_raw);
+  float* sA_lo = sA_hi + C::A_FLOATS;
+  float* sB_hi = sA_lo + C::A_FLOATS;
+  float* sB_lo = sB_hi + C::B_FLOATS;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sB_lo + C::B_FLOATS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int strips = (a.W + TC_M - 1) / TC_M;
+  const int x0 = (blockIdx.x % strips) * TC_M;
+  const int y0 = (blockIdx.x / strips) * R;
+  const int n = blockIdx.y;
+  const bool relu_in = (a.flags & RISP_CONV_RELU_IN) != 0;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) mbar_init(smem_u32(mbar), 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // instruction descriptor: D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2, K-major both, N>>3 [17,23), M>>4 [24,29)
+  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+  const int n_chunks = (a.CinG * 4 + CI_C - 1) / CI_C;
+  const long long row_stride = (long long)a.CinG * a.W * 4;              // floats per image row (blocked layout)
+  const float* xin = a.x + (long long)n * a.H * row_stride;
+  const float* min_ = a.mask_in ? a.mask_in + (long long)n * a.H * row_stride : nullptr;
+  const long long lo_off = (long long)n_chunks * C::B_CHUNK_FLOATS;
+  uint32_t phase = 0;
+  bool pending = false;      // a committed batch of MMAs may still be reading shared memory
+
+  for (int c = 0; c < n_chunks; ++c) {
+    // the previous batch of MMAs still reads shared memory: wait for its commit before restaging
+    if (pending) { mbar_wait(smem_u32(mbar), phase); phase ^= 1; pending = false; }
+    __syncthreads();
+    // ---- stage the input rows of this chunk (hi / lo split, zero padding, optional input ReLU / mask) ----
+    for (int i = tid; i < C::ROWS * C::KG * C::PW; i += TC_THREADS) {
+      const int px = i % C::PW;
+      const int kg = (i / C::PW) % C::KG;
+      const int row = i / (C::PW * C::KG);
+      const int gy = y0 - C::PAD + row, gx = x0 - C::PAD + px, gkg = c * C::KG + kg;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && gkg < a.CinG) {
+        const long long o = (long long)gy * row_stride + ((long long)gkg * a.W + gx) * 4;
+        v = __ldg(reinterpret_cast<const float4*>(xin + o));
+        if (min_) {
+          const float4 m = __ldg(reinterpret_cast<const float4*>(min_ + o));
+          v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f; v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+        }
+      }
+      if (relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      float4 hi, lo;
+      hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); lo.x = v.x - hi.x;
+      hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); lo.y = v.y - hi.y;
+      hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); lo.z = v.z - hi.z;
+      hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); lo.w = v.w - hi.w;
+      reinterpret_cast<float4*>(sA_hi)[i] = hi;
+      reinterpret_cast<float4*>(sA_lo)[i] = lo;
+    }
+    for (int dy0 = 0; dy0 < K; dy0 += DYB) {
+      // ---- stage DYB tap rows of this chunk's weights (hi and lo blocks are contiguous in wprep) ----
+      if (pending) { mbar_wait(smem_u32(mbar), phase); phase ^= 1; pending = false; }
+      {
+        const long long off = (long long)c * C::B_CHUNK_FLOATS + (long long)dy0 * K * C::B_TAP_FLOATS;
+        const float4* gh = reinterpret_cast<const float4*>(a.wprep + off);
+        const float4* gl = reinterpret_cast<const float4*>(a.wprep + lo_off + off);
+        for (int i = tid; i < C::B_FLOATS / 4; i += TC_THREADS) {
+          reinterpret_cast<float4*>(sB_hi)[i] = __ldg(gh + i);
+          reinterpret_cast<float4*>(sB_lo)[i] = __ldg(gl + i);
+        }
+      }
+      fence_async_smem();      // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+#pragma unroll 1
+        for (int dyl = 0; dyl < DYB; ++dyl) {
+          const int dy = dy0 + dyl;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const uint32_t d_main = tmem_base + (uint32_t)(r * NP);
+            const uint32_t d_cross = tmem_base + (uint32_t)((R + r) * NP);
+            const uint32_t a_row = (uint32_t)((r + dy) * C::A_ROW_FLOATS * 4);
+#pragma unroll
+            for (int dx = 0; dx < K; ++dx) {
+#pragma unroll
+              for (int ks = 0; ks < C::KG / 2; ++ks) {
+                const uint32_t a_off = a_row + (uint32_t)((2 * ks) * C::PW * 16 + dx * 16);
+                const uint32_t b_off = (uint32_t)(((dyl * K + dx) * C::KG + 2 * ks) * NP * 16);
+                const uint64_t dAh = make_desc(smem_u32(sA_hi) + a_off, C::PW * 16, 128);
+                const uint64_t dAl = make_desc(smem_u32(sA_lo) + a_off, C::PW * 16, 128);
+                const uint64_t dBh = make_desc(smem_u32(sB_hi) + b_off, NP * 16, 128);
+                const uint64_t dBl = make_desc(smem_u32(sB_lo) + b_off, NP * 16, 128);
+                const uint32_t acc = (c == 0 && dy == 0 && dx == 0 && ks == 0) ? 0u : 1u;
+                umma_tf32(d_main, dAh, dBh, idesc, acc);
+                umma_tf32(d_cross, dAl, dBh, idesc, acc);
+                umma_tf32(d_cross, dAh, dBl, idesc, 1u);
+              }
+            }
+          }
+        }
+        umma_commit(smem_u32(mbar));
+      }
+      pending = true;
+    }
+  }
+  // ---- epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).., and the (w/4)-th half of the 16-column groups ----
+  mbar_wait(smem_u32(mbar), phase);
+  tc_fence_after();
+  const bool relu_out = (a.flags & RISP_CONV_RELU_OUT) != 0, add_res = (a.flags & RISP_CONV_ADD_RES) != 0,
+             res_relu = (a.flags & RISP_CONV_RES_RELU) != 0;
+  const int lq = warp & 3, half = warp >> 2;
+  const int gx = x0 + lq * 32 + lane;
+  const int CoutG = a.CoutPad / 4;
+  const long long orow = (long long)CoutG * a.W * 4;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int gy = y0 + r;                              // warp-uniform
+#pragma unroll
+    for (int cb = 0; cb < NP / 16; ++cb) {
+      if ((cb & 1) != half && NP > 16) continue;        // split the column groups between the two warp sets
+      if (NP == 16 && half != 0) continue;
+      float v[16], vc[16];
+      tmem_ld<16>(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(r * NP + cb * 16), v);
+      tmem_ld<16>(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)((R + r) * NP + cb * 16), vc);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) v[q] += vc[q];
+      if (gy < a.H && gx < a.W) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int co = cb * 16 + q * 4;
+          float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          if (a.bias) {
+            if (co < a.Cout) o.x += __ldg(a.bias + co);
+            if (co + 1 < a.Cout) o.y += __ldg(a.bias + co + 1);
+            if (co + 2 < a.Cout) o.z += __ldg(a.bias + co + 2);
+            if (co + 3 < a.Cout) o.w += __ldg(a.bias + co + 3);
+          }
+          if (relu_out) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          const long long ob = ((long long)n * a.H + gy) * orow + ((long long)(co / 4) * a.W + gx) * 4;
+          if (add_res) {
+            float4 rr = __ldg(reinterpret_cast<const float4*>(a.res + ob));
+            if (res_relu) { rr.x = fmaxf(rr.x, 0.f); rr.y = fmaxf(rr.y, 0.f); rr.z = fmaxf(rr.z, 0.f); rr.w = fmaxf(rr.w, 0.f); }
+            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+          }
+          if (a.mask_out) {
+            const float4 m = __ldg(reinterpret_cast<const float4*>(a.mask_out + ob));
+            o.x = m.x > 0.f ? o.x : 0.f; o.y = m.y > 0.f ? o.y : 0.f; o.z = m.z > 0.f ? o.z : 0.f; o.w = m.w > 0.f ? o.w : 0.f;
+          }
+          if (a.y_blk) *reinterpret_cast<float4*>(a.y_blk + ob) = o;
+          if (a.y_pln) {
+            const long long plane = (long long)a.H * a.W;
+            float* pp = a.y_pln + ((long long)n * a.Cout + co) * plane + (long long)gy * a.W + gx;
+            if (co < a.Cout) pp[0] = o.x;
+            if (co + 1 < a.Cout) pp[plane] = o.y;
+            if (co + 2 < a.Cout) pp[2 * plane] = o.z;
+            if (co + 3 < a.Cout) pp[3 * plane] = o.w;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// weights (Cout,Cin,K,K) -> [chunk][dy][dx][kg][NP][4] hi block, then lo block.  transpose_flip: data-gradient operator.
+__global__ void conv_tc_prepare_kernel(const float* __restrict__ w, float* __restrict__ out, int Cin, int Cout, int K, int CI_C,
+                                       int NP, int transpose_flip, long long total) {
+  const int rows = transpose_flip ? Cout : Cin, cols = transpose_flip ? Cin : Cout;   // rows = GEMM-K channels, cols = GEMM-N
+  const int KG = CI_C / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int j = (int)(t % 4); t /= 4;
+    const int co = (int)(t % NP); t /= NP;
+    const int kg = (int)(t % KG); t /= KG;
+    const int dx = (int)(t % K); t /= K;
+    const int dy = (int)(t % K); t /= K;
+    const int chunk = (int)t;
+    const int ci = chunk * CI_C + kg * 4 + j;
+    float v = 0.f;
+    if (ci < rows && co < cols) {
+      if (!transpose_flip) v = w[(((long long)co * Cin + ci) * K + dy) * K + dx];
+      else v = w[(((long long)ci * Cin + co) * K + (K - 1 - dy)) * K + (K - 1 - dx)];
+    }
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    out[i] = hi;
+    out[total + i] = v - hi;
+  }
+}
+
+// planar (N,C,H,W) <-> blocked (N,H,CG,W,4), channels zero-padded to 4*CG
+__global__ void to_blocked_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int CG, int H, int W, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    long long t = i / W;
+    const int g = (int)(t % CG); t /= CG;
+    const int y = (int)(t % H);
+    const long long n = t / H;
+    const long long plane = (long long)H * W;
+    float4 o;
+    const float* p = src + (n * C + 4 * g) * plane + (long long)y * W + x;
+    o.x = (4 * g < C) ? p[0] : 0.f; o.y = (4 * g + 1 < C) ? p[plane] : 0.f;
+    o.z = (4 * g + 2 < C) ? p[2 * plane] : 0.f; o.w = (4 * g + 3 < C) ? p[3 * plane] : 0.f;
+    reinterpret_cast<float4*>(dst)[i] = o;
+  }
+}
+__global__ void from_blocked_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int CG, int H, int W, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    long long t = i / W;
+    const int g = (int)(t % CG); t /= CG;
+    const int y = (int)(t % H);
+    const long long n = t / H;
+    const long long plane = (long long)H * W;
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    float* p = dst + (n * C + 4 * g) * plane + (long long)y * W + x;
+    if (4 * g < C) p[0] = v.x;
+    if (4 * g + 1 < C) p[plane] = v.y;
+    if (4 * g + 2 < C) p[2 * plane] = v.z;
+    if (4 * g + 3 < C) p[3 * plane] = v.w;
+  }
+}
+
+template <int K, int CI_C, int R, int NP, int DYB>
+static int launch_tc(const ConvTcArgs& a, int N, cudaStream_t st) {
+  using C = TcCfg<K, CI_C, R, NP, DYB>;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(conv_tc_kernel<K, CI_C, R, NP, DYB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess) {
+      set_error("conv_tc: cannot opt in to %zu bytes of shared memory", C::SMEM);
+      return RISP_E_CUDA;
+    }
+    attr = true;
+  }
+  dim3 grid((unsigned)(cdiv(a.W, TC_M) * cdiv(a.H, R)), (unsigned)N);
+  conv_tc_kernel<K, CI_C, R, NP, DYB><<<grid, TC_THREADS, C::SMEM, st>>>(a);
+  return check_launch("conv_tc_kernel");
+}
+
+static int tc_chunk(int K) { (void)K; return 8; }
+
+}  // namespace risp
+
+using namespace risp;
+
+extern "C" int risp_conv_tc_supported(int Cin, int Cout, int K) {
+  return (K == 1 || K == 3 || K == 5 || K == 9) && Cout <= 64 && Cin >= 1;
+}
+
+extern "C" int risp_conv_tc_padded_channels(int C) { return (C + 15) / 16 * 16; }
+
+extern "C" size_t risp_conv_tc_weight_floats(int Cin, int Cout, int K, int transpose_flip) {
+  const int rows = transpose_flip ? Cout : Cin, cols = transpose_flip ? Cin : Cout;
+  const int CI_C = tc_chunk(K), NP = (cols + 15) / 16 * 16;
+  const int chunks = (((rows + 15) / 16 * 16) + CI_C - 1) / CI_C;
+  return (size_t)2 * chunks * K * K * (CI_C / 4) * NP * 4;
+}
+
+extern "C" int risp_conv_tc_prepare_weights(const float* weight, float* out, int Cin, int Cout, int K, int transpose_flip,
+                                            risp_stream_t stream) {
+  RISP_REQUIRE(weight && out && risp_conv_tc_supported(transpose_flip ? Cout : Cin, transpose_flip ? Cin : Cout, K), RISP_E_INVALID,
+               "risp_conv_tc_prepare_weights: unsupported shape");
+  const long long total = (long long)risp_conv_tc_weight_floats(Cin, Cout, K, transpose_flip) / 2;
+  const int cols = transpose_flip ? Cin : Cout;
+  conv_tc_prepare_kernel<<<(int)cdiv(total, 256), 256, 0, as_stream(stream)>>>(weight, out, Cin, Cout, K, tc_chunk(K),
+                                                                             (cols + 15) / 16 * 16, transpose_flip, total);
+  return check_launch("conv_tc_prepare_kernel");
+}
+
+extern "C" int risp_to_blocked(const float* planar, float* blocked, int N, int C, int CG, int H, int W, risp_stream_t stream) {
+  RISP_REQUIRE(planar && blocked && N > 0 && C > 0 && CG * 4 >= C && H > 0 && W > 0, RISP_E_INVALID, "risp_to_blocked: bad arguments");
+  const long long total = (long long)N * H * CG * W;
+  to_blocked_kernel<<<(int)(cdiv(total, 256) > 148 * 32 ? 148 * 32 : cdiv(total, 256)), 256, 0, as_stream(stream)>>>(planar, blocked, C, CG, H, W, total);
+  return check_launch("to_blocked_kernel");
+}
+
+extern "C" int risp_from_blocked(const float* blocked, float* planar, int N, int C, int CG, int H, int W, risp_stream_t stream) {
+  RISP_REQUIRE(planar && blocked && N > 0 && C > 0 && CG * 4 >= C && H > 0 && W > 0, RISP_E_INVALID, "risp_from_blocked: bad arguments");
+  const long long total = (long long)N * H * CG * W;
+  from_blocked_kernel<<<(int)(cdiv(total, 256) > 148 * 32 ? 148 * 32 : cdiv(total, 256)), 256, 0, as_stream(stream)>>>(blocked, planar, C, CG, H, W, total);
+  return check_launch("from_blocked_kernel");
+}
+
+// x, res, y_blk in the blocked layout with channel groups CinG = pad16(Cin)/4, CoutG = pad16(Cout)/4
+extern "C" int risp_conv_tc_fwd(const float* x_blk, const float* mask_in_blk, const float* wprep, const float* bias,
+                                const float* res_blk, const float* mask_out_blk, float* y_blk, float* y_planar, int N, int Cin,
+                                int Cout, int H, int W, int K, int flags, risp_stream_t stream) {
+  RISP_REQUIRE(x_blk && wprep && (y_blk || y_planar) && N > 0 && H > 0 && W > 0 && N <= 65535, RISP_E_INVALID,
+               "risp_conv_tc_fwd: bad arguments");
+  RISP_REQUIRE(risp_conv_tc_supported(Cin, Cout, K), RISP_E_UNSUPPORTED, "risp_conv_tc_fwd: unsupported shape %d->%d k%d", Cin, Cout, K);
+  RISP_REQUIRE(!(flags & RISP_CONV_ADD_RES) || res_blk, RISP_E_INVALID, "risp_conv_tc_fwd: ADD_RES without a residual");
+  const int NP = (Cout + 15) / 16 * 16;
+  ConvTcArgs a{x_blk, wprep, bias, res_blk, mask_in_blk, mask_out_blk, y_blk, y_planar, risp_conv_tc_padded_channels(Cin) / 4, Cout, NP, H, W, flags};
+  cudaStream_t st = as_stream(stream);
+#define RISP_TC(KK, RR, NN, DD) return launch_tc<KK, 8, RR, NN, DD>(a, N, st)
+  // rows per CTA: 2*R*NP TMEM columns <= 256 and shared memory <= ~100 KB so that two CTAs are resident per SM
+  // (one stages while the other multiplies); DYB = tap rows of weights staged per batch of MMAs
+  switch (K) {
+    case 1:
+      switch (NP) { case 16: RISP_TC(1, 8, 16, 1); case 32: RISP_TC(1, 4, 32, 1); case 48: RISP_TC(1, 2, 48, 1); default: RISP_TC(1, 2, 64, 1); }
+    case 3:
+      switch (NP) { case 16: RISP_TC(3, 8, 16, 3); case 32: RISP_TC(3, 4, 32, 3); case 48: RISP_TC(3, 2, 48, 3); default: RISP_TC(3, 2, 64, 3); }
+    case 5:
+      switch (NP) { case 16: RISP_TC(5, 4, 16, 5); case 32: RISP_TC(5, 4, 32, 1); case 48: RISP_TC(5, 2, 48, 1); default: RISP_TC(5, 2, 64, 1); }
+    default:
+      switch (NP) { case 16: RISP_TC(9, 2, 16, 3); case 32: RISP_TC(9, 2, 32, 1); case 48: RISP_TC(9, 2, 48, 1); default: RISP_TC(9, 2, 64, 1); }
+  }
+#undef RISP_TC
+}

@@ -13,3 +13,18 @@ def conv2d(x, weight, bias=None, relu_in=False, relu_out=False, residual=None, r
     if not x.is_cuda:
         raise RuntimeError('reconfigisp_b200 CNN candidates run on CUDA tensors only (no CPU fallback)')
     return ops.conv2d(x, weight, bias, relu_in, relu_out, residual, residual_relu)
+
+
+# ---- tensor-core path on channel-blocked activations (csrc/risp_conv_tc.cu) -------------------------------
+def to_blocked(x):
+    return ops.to_blocked(x)
+
+
+def from_blocked(xb, channels):
+    return ops.from_blocked(xb, channels)
+
+
+def conv2d_blocked(xb, weight, bias=None, relu_in=False, relu_out=False, residual=None, residual_relu=False):
+    """Same contract as `conv2d`, but input / residual / output are channel-blocked (N,H,C16/4,W,4) tensors and
+    the arithmetic runs on the tcgen05 tensor cores (3-term TF32 split, fp32-accurate)."""
+    return ops.conv2d_tc(xb, weight, bias, relu_in, relu_out, residual, residual_relu)

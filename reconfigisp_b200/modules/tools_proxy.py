@@ -64,9 +64,10 @@ class SRCNNRes(nn.Module):
             raise ValueError(feat_min.size(), None if param_vec is None else param_vec.size())
         feat_in = torch.cat([x, feat.view(N, -1, 1, 1).expand(N, feat.shape[1], H, W)], dim=1)
         c1, c2, c3 = self.srcnn[0], self.srcnn[2], self.srcnn[4]
-        h = conv.conv2d(feat_in, c1.weight, c1.bias, relu_out=True)
-        h = conv.conv2d(h, c2.weight, c2.bias, relu_out=True)
-        return conv.conv2d(h, c3.weight, c3.bias, residual=x)
+        h = conv.conv2d_blocked(conv.to_blocked(feat_in), c1.weight, c1.bias, relu_out=True)
+        h = conv.conv2d_blocked(h, c2.weight, c2.bias, relu_out=True)
+        h = conv.conv2d_blocked(h, c3.weight, c3.bias, residual=conv.to_blocked(x))
+        return conv.from_blocked(h, 3)
 
 
 class SRCNNDemosaic(nn.Module):
@@ -84,10 +85,10 @@ class SRCNNDemosaic(nn.Module):
             N, _, h2, w2 = h.shape
             h = torch.cat([h, param_vec.view(N, -1, 1, 1).expand(N, param_vec.shape[1], h2, w2)], dim=1)
         c1, c2, c3 = self.srcnn[0], self.srcnn[2], self.srcnn[4]
-        h = conv.conv2d(h, c1.weight, c1.bias, relu_out=True)
-        h = conv.conv2d(h, c2.weight, c2.bias, relu_out=True)
-        h = conv.conv2d(h, c3.weight, c3.bias)
-        return ops.pixel_shuffle2(h)
+        h = conv.conv2d_blocked(conv.to_blocked(h), c1.weight, c1.bias, relu_out=True)
+        h = conv.conv2d_blocked(h, c2.weight, c2.bias, relu_out=True)
+        h = conv.conv2d_blocked(h, c3.weight, c3.bias)
+        return ops.pixel_shuffle2(conv.from_blocked(h, 12))
 
 
 class ResidualBlock(nn.Module):
@@ -101,17 +102,20 @@ class ResidualBlock(nn.Module):
         self.shortcut = shortcut
 
     def forward(self, x):
+        """x and the result are channel-blocked tensors (see modules/conv.py)."""
         c1, c2 = self.basic[1], self.basic[3]
-        t = conv.conv2d(x, c1.weight, c1.bias, relu_in=True, relu_out=True)
-        return conv.conv2d(t, c2.weight, c2.bias, residual=x, residual_relu=True)
+        t = conv.conv2d_blocked(x, c1.weight, c1.bias, relu_in=True, relu_out=True)
+        return conv.conv2d_blocked(t, c2.weight, c2.bias, residual=x, residual_relu=True)
 
 
 def _trunk(seq, h):
+    """planar in, planar out; the 14 layers in between stay in the channel-blocked tensor-core layout"""
     first, blocks, last = seq[0], seq[1], seq[3]
-    h = conv.conv2d(h, first.weight, first.bias)
+    hb = conv.conv2d_blocked(conv.to_blocked(h), first.weight, first.bias)
     for blk in blocks:
-        h = blk(h)
-    return conv.conv2d(h, last.weight, last.bias, relu_in=True)
+        hb = blk(hb)
+    hb = conv.conv2d_blocked(hb, last.weight, last.bias, relu_in=True)
+    return conv.from_blocked(hb, last.weight.shape[0])
 
 
 class Path14lBayer(nn.Module):

@@ -676,3 +676,110 @@ class _ConvFn(torch.autograd.Function):
 
 def conv2d(x, weight, bias=None, relu_in=False, relu_out=False, residual=None, residual_relu=False):
     return _ConvFn.apply(x, residual, weight, bias, relu_in, relu_out, residual_relu)
+
+
+# ---- tensor-core convolution on channel-blocked activations (csrc/risp_conv_tc.cu) ------------------------
+def tc_groups(C):
+    """number of 4-channel groups of the blocked layout (channels padded to a multiple of 16)."""
+    return L.size('risp_conv_tc_padded_channels', C) // 4
+
+
+class _ToBlockedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _img(x)
+        N, C, H, W = x.shape
+        CG = tc_groups(C)
+        out = torch.empty((N, H, CG, W, 4), device=x.device, dtype=torch.float32)
+        L.call('risp_to_blocked', L.ptr(x), L.ptr(out), N, C, CG, H, W, L.stream())
+        ctx.C = C
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        return _FromBlockedFn.apply(d.contiguous(), ctx.C)
+
+
+class _FromBlockedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xb, C):
+        xb = xb.contiguous()
+        N, H, CG, W, _ = xb.shape
+        out = torch.empty((N, C, H, W), device=xb.device, dtype=torch.float32)
+        L.call('risp_from_blocked', L.ptr(xb), L.ptr(out), N, C, CG, H, W, L.stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        return _ToBlockedFn.apply(d.contiguous()), None
+
+
+def to_blocked(x): return _ToBlockedFn.apply(x)
+def from_blocked(xb, C): return _FromBlockedFn.apply(xb, C)
+
+
+def _tc_weights(weight, transpose_flip):
+    cache = getattr(weight, '_risp_wtc', None)
+    key = (bool(transpose_flip), weight._version, weight.data_ptr())
+    if cache is None or key not in cache:
+        Cout, Cin, K, _ = weight.shape
+        n = L.size('risp_conv_tc_weight_floats', Cin, Cout, K, int(transpose_flip))
+        wk = torch.empty((n,), device=weight.device, dtype=torch.float32)
+        L.call('risp_conv_tc_prepare_weights', L.ptr(weight.detach().contiguous()), L.ptr(wk), Cin, Cout, K, int(transpose_flip), L.stream())
+        if cache is None or len(cache) > 8:
+            cache = {}
+        cache[key] = wk
+        try:
+            weight._risp_wtc = cache
+        except Exception:
+            pass
+    return cache[key]
+
+
+def _conv_tc_raw(xb, mask_in, wk, bias, resb, mask_out, Cin, Cout, K, flags):
+    N, H, _, W, _ = xb.shape
+    yb = torch.empty((N, H, tc_groups(Cout), W, 4), device=xb.device, dtype=torch.float32)
+    L.call('risp_conv_tc_fwd', L.ptr(xb), L.ptr(mask_in), L.ptr(wk), L.ptr(bias), L.ptr(resb), L.ptr(mask_out), L.ptr(yb), None,
+           N, Cin, Cout, H, W, K, int(flags), L.stream())
+    return yb
+
+
+class _ConvTcFn(torch.autograd.Function):
+    """Blocked-layout convolution on the tensor cores; same contract as `_ConvFn` (data gradients only)."""
+
+    @staticmethod
+    def forward(ctx, xb, resb, weight, bias, relu_in, relu_out, res_relu):
+        xb = xb.contiguous()
+        Cout, Cin, K, _ = weight.shape
+        assert xb.shape[2] == tc_groups(Cin), 'blocked input has %d groups, weight expects %d' % (xb.shape[2], tc_groups(Cin))
+        assert not (relu_out and resb is not None)
+        flags = (CONV_RELU_IN if relu_in else 0) | (CONV_RELU_OUT if relu_out else 0)
+        if resb is not None:
+            resb = resb.contiguous()
+            flags |= CONV_ADD_RES | (CONV_RES_RELU if res_relu else 0)
+        b = None if bias is None else bias.detach().float().contiguous()
+        yb = _conv_tc_raw(xb, None, _tc_weights(weight, False), b, resb, None, Cin, Cout, K, flags)
+        ctx.cfg = (relu_in, relu_out, res_relu, Cin, Cout, K)
+        ctx.save_for_backward(xb if relu_in else None, yb if relu_out else None, resb if (resb is not None and res_relu) else None, weight)
+        ctx.has_res = resb is not None
+        return yb
+
+    @staticmethod
+    def backward(ctx, dyb):
+        xb, yb, resb, weight = ctx.saved_tensors
+        relu_in, relu_out, res_relu, Cin, Cout, K = ctx.cfg
+        dyb = dyb.contiguous()
+        dxb = dres = None
+        if ctx.needs_input_grad[0]:
+            dxb = _conv_tc_raw(dyb, yb if relu_out else None, _tc_weights(weight, True), None, None, xb if relu_in else None,
+                               Cout, Cin, K, 0)
+        if ctx.has_res and ctx.needs_input_grad[1]:
+            dres = dyb if not res_relu else dyb * (resb > 0).to(dyb.dtype)
+        if weight.requires_grad and ctx.needs_input_grad[2]:
+            raise NotImplementedError('weight gradients of the candidate nets (proxy fine-tuning, SURVEY §8f) are not built yet')
+        return dxb, dres, None, None, None, None, None
+
+
+def conv2d_tc(xb, weight, bias=None, relu_in=False, relu_out=False, residual=None, residual_relu=False):
+    """Blocked in, blocked out."""
+    return _ConvTcFn.apply(xb, residual, weight, bias, relu_in, relu_out, residual_relu)

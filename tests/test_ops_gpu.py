@@ -442,3 +442,34 @@ def test_decode_codes_matches_loader_normalisation(ops):
     assert torch.equal(ops.decode_codes(gt.to(torch.uint8).cuda(), 255.).cpu(), gt.float() / 255.)
     big = torch.randint(0, 16384, (1, 1, 64, 128), generator=g, dtype=torch.int32)
     assert torch.equal(ops.decode_codes(big.to(torch.int16).cuda(), 16383.).cpu(), big.float() / 16383.)
+
+
+@pytest.mark.parametrize('cfg', [(3, 64, 64, 3), (2, 15, 64, 9), (2, 64, 32, 5), (2, 32, 3, 5), (2, 64, 32, 1), (1, 4, 64, 3), (2, 64, 4, 3), (1, 32, 12, 5)])
+def test_conv2d_tensor_core_path(ops, cfg):
+    """tcgen05 implicit-GEMM convolution (3-term TF32 split) against torch's fp64 convolution on the CPU."""
+    import torch.nn.functional as F
+    N, Cin, Cout, K = cfg
+    for H, W in ((23, 40), (37, 300)):
+        g = torch.Generator().manual_seed(77 + K + Cin)
+        x = torch.randn(N, Cin, H, W, generator=g)
+        w = torch.randn(Cout, Cin, K, K, generator=g) * (1.0 / (K * Cin ** 0.5))
+        b = torch.randn(Cout, generator=g) * 0.1
+        res = torch.randn(N, Cout, H, W, generator=g)
+        d = torch.randn(N, Cout, H, W, generator=g)
+        for relu_in, relu_out, use_res, res_relu in ((False, False, False, False), (True, True, False, False), (True, False, True, True)):
+            xo, ro = x.double().requires_grad_(), res.double().requires_grad_()
+            yo = F.conv2d(torch.relu(xo) if relu_in else xo, w.double(), b.double(), padding=K // 2)
+            if relu_out:
+                yo = torch.relu(yo)
+            if use_res:
+                yo = yo + (torch.relu(ro) if res_relu else ro)
+            go = torch.autograd.grad(yo, (xo, ro) if use_res else (xo,), d.double())
+            xg, rg = dev(x).requires_grad_(), dev(res).requires_grad_()
+            yb = ops.conv2d_tc(ops.to_blocked(xg), dev(w), dev(b), relu_in, relu_out, ops.to_blocked(rg) if use_res else None, res_relu)
+            yg = ops.from_blocked(yb, Cout)
+            gg = torch.autograd.grad(yg, (xg, rg) if use_res else (xg,), dev(d))
+            # the tensor core rounds its accumulator toward zero once per MMA: the error grows with the number of
+            # chained MMAs (taps x channels / 8) and is RELATIVE to the accumulated magnitude
+            assert maxabs(yg, yo) <= 4e-5 * max(1.0, float(yo.abs().max())), (cfg, H, W, relu_in, relu_out, use_res, maxabs(yg, yo))
+            for a, bb in zip(gg, go):
+                assert maxabs(a, bb) <= 1.5e-4 * max(1.0, float(bb.abs().max())), (cfg, H, W, relu_in, relu_out, use_res, maxabs(a, bb))
