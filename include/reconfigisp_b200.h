@@ -273,6 +273,10 @@ int risp_conv_tc_fwd(const float* x_blk, const float* mask_in_blk, const float* 
                      const float* res_blk, const float* mask_out_blk, float* y_blk, float* y_planar, int N, int Cin,
                      int Cout, int H, int W, int K, int flags, risp_stream_t stream);
 
+/* Diagnostic: cycles to issue / complete `iters` tcgen05 tf32 MMAs (M=128, N=NP, K=8) from one thread with the
+ * operand layout of risp_conv_tc_fwd.  out: DEVICE long long[2] = {issue cycles, total cycles}. */
+int risp_debug_mma_rate(long long* out, int NP, int iters, int n_acc, int split3, risp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
   for (uint32_t spin = 0; !mbar_try(mbar, parity); ++spin)
     if (spin > (1u << 24)) __trap();
 }
+// one elected lane of a fully converged warp (ptxas keeps the MMA operands in uniform registers and emits a
+// plain predicated UTCHMMA; under an ordinary `tid == 0` branch it wraps every MMA in an ELECT / BRA.U.ANY loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -193,7 +200,8 @@ conv_tc_kernel(ConvTcArgs a) {
       fence_async_smem();      // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0) {
+       if (elect_one()) {
         tc_fence_after();
 #pragma unroll 1
         for (int dyl = 0; dyl < DYB; ++dyl) {
@@ -222,6 +230,8 @@ conv_tc_kernel(ConvTcArgs a) {
           }
         }
         umma_commit(smem_u32(mbar));
+       }
+       __syncwarp();
       }
       pending = true;
     }
@@ -432,4 +442,62 @@ extern "C" int risp_conv_tc_fwd(const float* x_blk, const float* mask_in_blk, co
       switch (NP) { case 16: RISP_TC(9, 2, 16, 3); case 32: RISP_TC(9, 2, 32, 1); case 48: RISP_TC(9, 2, 48, 1); default: RISP_TC(9, 2, 64, 1); }
   }
 #undef RISP_TC
+}
+
+// ---- micro-benchmark: raw tcgen05 tf32 issue / execution rate for the operand layout used above ---------------
+namespace risp {
+template <int NP>
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(long long* out, int iters, int n_acc, int split3) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* sA = reinterpret_cast<float*>(smem_raw);          // 2 kgroups x 136 px x 4
+  float* sB = sA + 2 * 136 * 4 * 2;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sB + 2 * NP * 4 * 2);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  for (int i = threadIdx.x; i < 2 * 136 * 4 * 2 + 2 * NP * 4 * 2; i += 128) sA[i] = 0.001f * (i & 63);
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 0) mbar_init(smem_u32(mbar), 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = *slot;
+  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  if (threadIdx.x == 0) {
+    const uint64_t dA = make_desc(smem_u32(sA), 136 * 16, 128), dA2 = make_desc(smem_u32(sA + 2 * 136 * 4), 136 * 16, 128);
+    const uint64_t dB = make_desc(smem_u32(sB), NP * 16, 128), dB2 = make_desc(smem_u32(sB + 2 * NP * 4), NP * 16, 128);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      const uint32_t d = tb + (uint32_t)((i % n_acc) * NP);
+      umma_tf32(d, dA + (uint64_t)(i & 3), dB, idesc, i >= n_acc ? 1u : 0u);
+      if (split3) {
+        umma_tf32(d, dA2 + (uint64_t)(i & 3), dB, idesc, 1u);
+        umma_tf32(d, dA + (uint64_t)(i & 3), dB2, idesc, 1u);
+      }
+    }
+    const long long t1 = clock64();
+    umma_commit(smem_u32(mbar));
+    mbar_wait(smem_u32(mbar), 0);
+    const long long t2 = clock64();
+    out[0] = t1 - t0; out[1] = t2 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tb) : "memory");
+}
+}  // namespace risp
+
+// out: DEVICE long long[2] = {issue cycles, total cycles}.  Diagnostic entry (scripts/probe_mma_rate.py).
+extern "C" int risp_debug_mma_rate(long long* out, int NP, int iters, int n_acc, int split3, risp_stream_t stream) {
+  RISP_REQUIRE(out && (NP == 64 || NP == 128 || NP == 256) && iters > 0 && n_acc >= 1 && n_acc * NP <= 512, RISP_E_INVALID,
+               "risp_debug_mma_rate: bad arguments");
+  const size_t smem = 64 * 1024;
+  cudaStream_t st = as_stream(stream);
+  if (NP == 64) { cudaFuncSetAttribute(mma_rate_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); mma_rate_kernel<64><<<1, 128, smem, st>>>(out, iters, n_acc, split3); }
+  else if (NP == 128) { cudaFuncSetAttribute(mma_rate_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); mma_rate_kernel<128><<<1, 128, smem, st>>>(out, iters, n_acc, split3); }
+  else { cudaFuncSetAttribute(mma_rate_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); mma_rate_kernel<256><<<1, 128, smem, st>>>(out, iters, n_acc, split3); }
+  return check_launch("mma_rate_kernel");
 }
