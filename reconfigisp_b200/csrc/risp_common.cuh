@@ -84,7 +84,7 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-__device__ __forceinline__ float sat01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
+__device__ __forceinline__ float sat01(float v) { return __saturatef(v); }   // one .SAT instruction (NaN -> 0)
 // torch.clamp backward mask is inclusive on both ends
 __device__ __forceinline__ float in01(float v) { return (v >= 0.f && v <= 1.f) ? 1.f : 0.f; }
 #endif

@@ -162,28 +162,43 @@ conv_tc_kernel(ConvTcArgs a) {
     if (pending) { mbar_wait(smem_u32(mbar), phase); phase ^= 1; pending = false; }
     __syncthreads();
     // ---- stage the input rows of this chunk (hi / lo split, zero padding, optional input ReLU / mask) ----
-    for (int i = tid; i < C::ROWS * C::KG * C::PW; i += TC_THREADS) {
-      const int px = i % C::PW;
-      const int kg = (i / C::PW) % C::KG;
-      const int row = i / (C::PW * C::KG);
-      const int gy = y0 - C::PAD + row, gx = x0 - C::PAD + px, gkg = c * C::KG + kg;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && gkg < a.CinG) {
-        const long long o = (long long)gy * row_stride + ((long long)gkg * a.W + gx) * 4;
-        v = __ldg(reinterpret_cast<const float4*>(xin + o));
-        if (min_) {
-          const float4 m = __ldg(reinterpret_cast<const float4*>(min_ + o));
-          v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f; v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+    // all global loads of the phase are issued first (ITER independent 128-bit loads per thread), then split and
+    // stored: otherwise every thread pays the L2 latency once per element it stages
+    {
+      constexpr int TOTAL = C::ROWS * C::KG * C::PW;
+      constexpr int ITER = (TOTAL + TC_THREADS - 1) / TC_THREADS;
+      float4 v[ITER], m[ITER];
+#pragma unroll
+      for (int it = 0; it < ITER; ++it) {
+        const int i = tid + it * TC_THREADS;
+        const int px = i % C::PW;
+        const int kg = (i / C::PW) % C::KG;
+        const int row = i / (C::PW * C::KG);
+        const int gy = y0 - C::PAD + row, gx = x0 - C::PAD + px, gkg = c * C::KG + kg;
+        v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        m[it] = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (i < TOTAL && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && gkg < a.CinG) {
+          const long long o = (long long)gy * row_stride + ((long long)gkg * a.W + gx) * 4;
+          v[it] = __ldg(reinterpret_cast<const float4*>(xin + o));
+          if (min_) m[it] = __ldg(reinterpret_cast<const float4*>(min_ + o));
         }
       }
-      if (relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-      float4 hi, lo;
-      hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); lo.x = v.x - hi.x;
-      hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); lo.y = v.y - hi.y;
-      hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); lo.z = v.z - hi.z;
-      hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); lo.w = v.w - hi.w;
-      reinterpret_cast<float4*>(sA_hi)[i] = hi;
-      reinterpret_cast<float4*>(sA_lo)[i] = lo;
+#pragma unroll
+      for (int it = 0; it < ITER; ++it) {
+        const int i = tid + it * TC_THREADS;
+        float4 t = v[it];
+        if (min_) { t.x = m[it].x > 0.f ? t.x : 0.f; t.y = m[it].y > 0.f ? t.y : 0.f; t.z = m[it].z > 0.f ? t.z : 0.f; t.w = m[it].w > 0.f ? t.w : 0.f; }
+        if (relu_in) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+        float4 hi, lo;
+        hi.x = __uint_as_float(__float_as_uint(t.x) & 0xffffe000u); lo.x = t.x - hi.x;
+        hi.y = __uint_as_float(__float_as_uint(t.y) & 0xffffe000u); lo.y = t.y - hi.y;
+        hi.z = __uint_as_float(__float_as_uint(t.z) & 0xffffe000u); lo.z = t.z - hi.z;
+        hi.w = __uint_as_float(__float_as_uint(t.w) & 0xffffe000u); lo.w = t.w - hi.w;
+        if (i < TOTAL) {
+          reinterpret_cast<float4*>(sA_hi)[i] = hi;
+          reinterpret_cast<float4*>(sA_lo)[i] = lo;
+        }
+      }
     }
     for (int dy0 = 0; dy0 < K; dy0 += DYB) {
       // ---- stage DYB tap rows of this chunk's weights (hi and lo blocks are contiguous in wprep) ----
@@ -192,9 +207,18 @@ conv_tc_kernel(ConvTcArgs a) {
         const long long off = (long long)c * C::B_CHUNK_FLOATS + (long long)dy0 * K * C::B_TAP_FLOATS;
         const float4* gh = reinterpret_cast<const float4*>(a.wprep + off);
         const float4* gl = reinterpret_cast<const float4*>(a.wprep + lo_off + off);
-        for (int i = tid; i < C::B_FLOATS / 4; i += TC_THREADS) {
-          reinterpret_cast<float4*>(sB_hi)[i] = __ldg(gh + i);
-          reinterpret_cast<float4*>(sB_lo)[i] = __ldg(gl + i);
+        constexpr int BTOT = C::B_FLOATS / 4;
+        constexpr int BITER = (BTOT + TC_THREADS - 1) / TC_THREADS;
+        float4 bh[BITER], bl[BITER];
+#pragma unroll
+        for (int it = 0; it < BITER; ++it) {
+          const int i = tid + it * TC_THREADS;
+          if (i < BTOT) { bh[it] = __ldg(gh + i); bl[it] = __ldg(gl + i); }
+        }
+#pragma unroll
+        for (int it = 0; it < BITER; ++it) {
+          const int i = tid + it * TC_THREADS;
+          if (i < BTOT) { reinterpret_cast<float4*>(sB_hi)[i] = bh[it]; reinterpret_cast<float4*>(sB_lo)[i] = bl[it]; }
         }
       }
       fence_async_smem();      // generic-proxy smem writes -> visible to the tensor-core (async) proxy

@@ -84,12 +84,12 @@ __device__ __forceinline__ GtmCoef gtm_prepare(const float* __restrict__ p, int 
 }
 
 __device__ __forceinline__ float gtm_px(float x, const GtmCoef& c, int n) {
-  const float xc = fminf(fmaxf(x, 0.f), 1.f);
+  const float xc = __saturatef(x);
   float f = c.s0 * xc;
 #pragma unroll
   for (int k = 0; k < 4; ++k)
     if (k < n - 1) f = fmaf(c.ds[k], fmaxf(xc - c.xk[k], 0.f), f);
-  return fminf(fmaxf(f, 0.f), 1.f);
+  return __saturatef(f);
 }
 
 // backward: d (in: dL/dout, out: dL/dx) and the knot gradients via the hat basis
