@@ -257,6 +257,14 @@ int risp_conv2d_fwd(const float* x, const float* mask_in, const float* wk, const
                     const float* mask_out, float* y, int N, int Cin, int Cout, int H, int W, int K, int flags,
                     risp_stream_t stream);
 
+/* Weight gradient of the same convolution (proxy fine-tuning, darts_ft_model.py:206-246):
+ *   dW[co][ci][ky][kx] = sum dy'[n][co][y][x] * x'[n][ci][y+ky-P][x+kx-P],  dy' = dy*[mask_dy > 0], x' = relu?(x)
+ * dweight has the nn.Conv2d layout (Cout,Cin,K,K).  Deterministic (per-block partials + fixed-order finaliser). */
+size_t risp_conv2d_bwd_weight_workspace(int Cin, int Cout, int K);
+int risp_conv2d_bwd_weight(const float* x, const float* dy, const float* mask_dy, float* dweight, int N, int Cin,
+                           int Cout, int H, int W, int K, int relu_in, void* workspace, size_t workspace_bytes,
+                           risp_stream_t stream);
+
 /* Tensor-core path of the same convolution: implicit GEMM on tcgen05 (kind::tf32, TMEM accumulators) with a
  * 3-term hi/lo split so the result stays fp32-accurate (<= ~1e-6 relative), on CHANNEL-BLOCKED activations
  * (N, H, C16/4, W, 4) where C16 = channels padded to a multiple of 16 (risp_conv_tc_padded_channels).

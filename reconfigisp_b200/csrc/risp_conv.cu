@@ -227,3 +227,111 @@ extern "C" int risp_conv2d_fwd(const float* x, const float* mask_in, const float
     default: set_error("risp_conv2d_fwd: kernel size %d not in {1,3,5,9}", K); return RISP_E_UNSUPPORTED;
   }
 }
+
+// ---- weight gradient (proxy fine-tuning, darts_ft_model.py:206-246) -------------------------------------
+//   dW[co][ci][ky][kx] = sum_{n,y,x} dy'[n][co][y][x] * x'[n][ci][y+ky-P][x+kx-P],   dy' = dy*[mask_dy>0], x' = relu?(x)
+// A CTA owns one input channel, a block of 16 output channels and a strided set of 8x64 pixel tiles; thread
+// (co, ky) keeps the K partial sums over kx in registers.  Partials go to [tile_group][Cout][Cin][K*K] and are
+// finished by the deterministic finaliser (no float atomics).
+namespace risp {
+constexpr int WG_TY = 8, WG_TX = 64, WG_CO = 16, WG_GROUPS = 16;
+
+template <int K>
+__global__ void __launch_bounds__(WG_CO * K)
+conv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ mask_dy,
+                  float* __restrict__ partial, int N, int Cin, int Cout, int H, int W, int relu_in) {
+  constexpr int PAD = K / 2, XW = WG_TX + K - 1, XH = WG_TY + K - 1;
+  __shared__ float s_x[XH][XW];
+  __shared__ float s_dy[WG_CO][WG_TY][WG_TX];
+  const int ci = blockIdx.y, co0 = blockIdx.z * WG_CO;
+  const int co_l = threadIdx.x / K, ky = threadIdx.x % K;
+  const int tiles_x = (W + WG_TX - 1) / WG_TX, tiles_y = (H + WG_TY - 1) / WG_TY;
+  const int n_tiles = N * tiles_y * tiles_x;
+  const long long plane = (long long)H * W;
+  float acc[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k] = 0.f;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int n = t / (tiles_y * tiles_x);
+    const int y0 = ((t / tiles_x) % tiles_y) * WG_TY, x0 = (t % tiles_x) * WG_TX;
+    __syncthreads();
+    for (int i = threadIdx.x; i < XH * XW; i += blockDim.x) {
+      const int r = i / XW, c = i % XW;
+      const int gy = y0 - PAD + r, gx = x0 - PAD + c;
+      float v = 0.f;
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(x + ((long long)n * Cin + ci) * plane + (long long)gy * W + gx);
+      s_x[r][c] = relu_in ? fmaxf(v, 0.f) : v;
+    }
+    for (int i = threadIdx.x; i < WG_CO * WG_TY * WG_TX; i += blockDim.x) {
+      const int c = i % WG_TX, r = (i / WG_TX) % WG_TY, co = i / (WG_TX * WG_TY);
+      const int gy = y0 + r, gx = x0 + c;
+      float v = 0.f;
+      if (co0 + co < Cout && gy < H && gx < W) {
+        const long long o = ((long long)n * Cout + co0 + co) * plane + (long long)gy * W + gx;
+        v = __ldg(dy + o);
+        if (mask_dy) v = (__ldg(mask_dy + o) > 0.f) ? v : 0.f;
+      }
+      s_dy[co][r][c] = v;
+    }
+    __syncthreads();
+    for (int r = 0; r < WG_TY; ++r) {
+      float win[K];
+#pragma unroll
+      for (int k = 0; k < K - 1; ++k) win[k + 1] = s_x[r + ky][k];
+      for (int c = 0; c < WG_TX; ++c) {
+#pragma unroll
+        for (int k = 0; k < K - 1; ++k) win[k] = win[k + 1];
+        win[K - 1] = s_x[r + ky][c + K - 1];
+        const float g = s_dy[co_l][r][c];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = fmaf(g, win[k], acc[k]);
+      }
+    }
+  }
+  if (co0 + co_l < Cout) {
+    float* o = partial + (((long long)blockIdx.x * Cout + co0 + co_l) * Cin + ci) * K * K + ky * K;
+#pragma unroll
+    for (int k = 0; k < K; ++k) o[k] = acc[k];
+  }
+}
+
+__global__ void wgrad_final_kernel(const float* __restrict__ partial, float* __restrict__ dw, long long n, int groups) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int g = 0; g < groups; ++g) s += partial[(long long)g * n + i];
+    dw[i] = s;
+  }
+}
+
+template <int K>
+static int launch_wgrad(const float* x, const float* dy, const float* mask_dy, float* partial, float* dw, int N, int Cin,
+                        int Cout, int H, int W, int relu_in, cudaStream_t st) {
+  dim3 grid(WG_GROUPS, Cin, (Cout + WG_CO - 1) / WG_CO);
+  conv_wgrad_kernel<K><<<grid, WG_CO * K, 0, st>>>(x, dy, mask_dy, partial, N, Cin, Cout, H, W, relu_in);
+  const long long n = (long long)Cout * Cin * K * K;
+  wgrad_final_kernel<<<(int)cdiv(n, 256), 256, 0, st>>>(partial, dw, n, WG_GROUPS);
+  return check_launch("conv_wgrad_kernel");
+}
+}  // namespace risp
+
+extern "C" size_t risp_conv2d_bwd_weight_workspace(int Cin, int Cout, int K) {
+  return (size_t)risp::WG_GROUPS * Cout * Cin * K * K * sizeof(float);
+}
+
+extern "C" int risp_conv2d_bwd_weight(const float* x, const float* dy, const float* mask_dy, float* dweight, int N, int Cin,
+                                      int Cout, int H, int W, int K, int relu_in, void* workspace, size_t workspace_bytes,
+                                      risp_stream_t stream) {
+  RISP_REQUIRE(x && dy && dweight && N > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0, RISP_E_INVALID, "risp_conv2d_bwd_weight: bad arguments");
+  RISP_REQUIRE(Cin <= 65535 && Cout <= 16 * 65535, RISP_E_INVALID, "risp_conv2d_bwd_weight: too many channels");
+  RISP_REQUIRE(workspace && workspace_bytes >= risp_conv2d_bwd_weight_workspace(Cin, Cout, K), RISP_E_WORKSPACE,
+               "risp_conv2d_bwd_weight: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  float* partial = static_cast<float*>(workspace);
+  switch (K) {
+    case 1: return launch_wgrad<1>(x, dy, mask_dy, partial, dweight, N, Cin, Cout, H, W, relu_in, st);
+    case 3: return launch_wgrad<3>(x, dy, mask_dy, partial, dweight, N, Cin, Cout, H, W, relu_in, st);
+    case 5: return launch_wgrad<5>(x, dy, mask_dy, partial, dweight, N, Cin, Cout, H, W, relu_in, st);
+    case 9: return launch_wgrad<9>(x, dy, mask_dy, partial, dweight, N, Cin, Cout, H, W, relu_in, st);
+    default: set_error("risp_conv2d_bwd_weight: kernel size %d not in {1,3,5,9}", K); return RISP_E_UNSUPPORTED;
+  }
+}

@@ -655,6 +655,7 @@ class _ConvFn(torch.autograd.Function):
         ctx.cfg = (relu_in, relu_out, res_relu, Cin, K)
         ctx.save_for_backward(x if relu_in else None, y if relu_out else None, res if (res is not None and res_relu) else None, weight)
         ctx.has_res = res is not None
+        ctx.x_full = x if (weight.requires_grad or (bias is not None and bias.requires_grad)) else None
         return y
 
     @staticmethod
@@ -669,9 +670,33 @@ class _ConvFn(torch.autograd.Function):
                            Cin, K, 0)
         if ctx.has_res and ctx.needs_input_grad[1]:
             dres = dy if not res_relu else dy * (res > 0).to(dy.dtype)
-        if weight.requires_grad and ctx.needs_input_grad[2]:
-            raise NotImplementedError('weight gradients of the candidate nets (proxy fine-tuning, SURVEY §8f) are not built yet')
-        return dx, dres, None, None, None, None, None
+        dw = db = None
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            dw, db = conv_weight_grads(ctx.x_full, dy, y if relu_out else None, weight.shape, relu_in,
+                                       ctx.needs_input_grad[2], ctx.needs_input_grad[3])
+        return dx, dres, dw, db, None, None, None
+
+
+def conv_weight_grads(x, dy, y_mask, wshape, relu_in, want_w=True, want_b=True):
+    """dW (nn.Conv2d layout) and db of y = conv(relu?(x), W) + b for an upstream gradient dy (masked by [y_mask > 0])."""
+    Cout, Cin, K, _ = wshape
+    N, _, H, W = x.shape
+    dw = db = None
+    if want_w:
+        dw = torch.empty(tuple(wshape), device=x.device, dtype=torch.float32)
+        ws = L.workspace(L.size('risp_conv2d_bwd_weight_workspace', Cin, Cout, K), x.device)
+        L.call('risp_conv2d_bwd_weight', L.ptr(x.contiguous()), L.ptr(dy.contiguous()), L.ptr(y_mask), L.ptr(dw), N, Cin, Cout, H, W, K,
+               int(bool(relu_in)), L.ptr(ws), ws.numel() * 4, L.stream())
+    if want_b:
+        # db[co] = sum dy': a per-plane reduction (own kernel) + a (N,Cout) -> (Cout,) sum
+        dyb = dy if y_mask is None else chain_apply_mask(dy, y_mask)
+        db = plane_stats(dyb)[..., 1].sum(dim=0) * float(H * W)
+    return dw, db
+
+
+def chain_apply_mask(t, mask):
+    """t * [mask > 0] (tiny helper for the bias gradient; elementwise torch op on the fine-tune path only)."""
+    return t * (mask > 0).to(t.dtype)
 
 
 def conv2d(x, weight, bias=None, relu_in=False, relu_out=False, residual=None, residual_relu=False):
@@ -762,6 +787,7 @@ class _ConvTcFn(torch.autograd.Function):
         ctx.cfg = (relu_in, relu_out, res_relu, Cin, Cout, K)
         ctx.save_for_backward(xb if relu_in else None, yb if relu_out else None, resb if (resb is not None and res_relu) else None, weight)
         ctx.has_res = resb is not None
+        ctx.xb_full = xb if (weight.requires_grad or (bias is not None and bias.requires_grad)) else None
         return yb
 
     @staticmethod
@@ -775,9 +801,14 @@ class _ConvTcFn(torch.autograd.Function):
                                Cout, Cin, K, 0)
         if ctx.has_res and ctx.needs_input_grad[1]:
             dres = dyb if not res_relu else dyb * (resb > 0).to(dyb.dtype)
-        if weight.requires_grad and ctx.needs_input_grad[2]:
-            raise NotImplementedError('weight gradients of the candidate nets (proxy fine-tuning, SURVEY §8f) are not built yet')
-        return dxb, dres, None, None, None, None, None
+        dw = db = None
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            # fine-tuning path only: the weight-gradient kernel works on planar tensors
+            xp = _FromBlockedFn.apply(ctx.xb_full, Cin)
+            dyp = _FromBlockedFn.apply(dyb, Cout)
+            yp = _FromBlockedFn.apply(yb, Cout) if relu_out else None
+            dw, db = conv_weight_grads(xp, dyp, yp, weight.shape, relu_in, ctx.needs_input_grad[2], ctx.needs_input_grad[3])
+        return dxb, dres, dw, db, None, None, None
 
 
 def conv2d_tc(xb, weight, bias=None, relu_in=False, relu_out=False, residual=None, residual_relu=False):

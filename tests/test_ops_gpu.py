@@ -480,3 +480,35 @@ def test_conv2d_tensor_core_path(ops, cfg):
                     assert float((err > tol).double().mean()) <= 2e-3, (cfg, H, W, float((err > tol).double().mean()))
                 else:
                     assert float(err.max()) <= tol, (cfg, H, W, relu_in, relu_out, use_res, float(err.max()))
+
+
+@pytest.mark.parametrize('cfg', [(2, 15, 64, 9), (2, 64, 32, 5), (2, 32, 3, 5), (3, 5, 20, 3), (2, 7, 9, 1)])
+@pytest.mark.parametrize('path', ['direct', 'tc'])
+def test_conv2d_weight_and_bias_gradient(ops, cfg, path):
+    """Weight / bias gradients (proxy fine-tuning, darts_ft_model.py:206-246) against torch's fp64 autograd."""
+    import torch.nn.functional as F
+    N, Cin, Cout, K = cfg
+    H, W = 37, 70
+    g = torch.Generator().manual_seed(5 + K + Cin)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, K, K, generator=g) * (1.0 / (K * Cin ** 0.5))
+    b = torch.randn(Cout, generator=g) * 0.1
+    d = torch.randn(N, Cout, H, W, generator=g) / (H * W) ** 0.5
+    for relu_in, relu_out in ((False, False), (True, True)):
+        wo, bo = w.double().requires_grad_(), b.double().requires_grad_()
+        xo = x.double()
+        yo = F.conv2d(torch.relu(xo) if relu_in else xo, wo, bo, padding=K // 2)
+        if relu_out:
+            yo = torch.relu(yo)
+        gwo, gbo = torch.autograd.grad(yo, (wo, bo), d.double())
+        wg, bg = dev(w).requires_grad_(), dev(b).requires_grad_()
+        if path == 'direct':
+            yg = ops.conv2d(dev(x), wg, bg, relu_in, relu_out)
+        else:
+            yg = ops.from_blocked(ops.conv2d_tc(ops.to_blocked(dev(x)), wg, bg, relu_in, relu_out), Cout)
+        gw, gb = torch.autograd.grad(yg, (wg, bg), dev(d))
+        tw = 2e-5 * max(1.0, float(gwo.abs().max()))
+        # an output ReLU mask bit can flip for outputs within rounding distance of 0 (tensor-core path mostly)
+        errw = (gw.cpu().double() - gwo).abs()
+        assert float(errw.max()) <= (20 if relu_out else 1) * tw, (cfg, path, relu_in, float(errw.max()), tw)
+        assert maxabs(gb, gbo) <= (20 if relu_out else 1) * 2e-5 * max(1.0, float(gbo.abs().max())), (cfg, path, relu_in)
