@@ -34,6 +34,8 @@ def create_model(opt):
     model = opt['model']
     if model == 'darts':
         from .search import DartsModel as M
+    elif model == 'darts_ft':
+        from .search_ft import DartsFtModel as M
     elif model == 'isp':
         from .tuning import IspModel as M
     else:

@@ -618,8 +618,8 @@ def _prepared_weights(weight, transpose_flip):
         n = L.size('risp_conv2d_prepared_weight_floats', Cin, Cout, K, int(transpose_flip))
         wk = torch.empty((n,), device=weight.device, dtype=torch.float32)
         L.call('risp_conv2d_prepare_weights', L.ptr(weight.detach().contiguous()), L.ptr(wk), Cin, Cout, K, int(transpose_flip), L.stream())
-        if cache is None or len(cache) > 8:
-            cache = {}
+        if cache is None or any(k[1:] != key[1:] for k in cache):
+            cache = {}          # the weight was updated in place (fine-tuning): drop the stale layouts
         cache[key] = wk
         try:
             weight._risp_wk = cache
@@ -751,7 +751,7 @@ def _tc_weights(weight, transpose_flip):
         n = L.size('risp_conv_tc_weight_floats', Cin, Cout, K, int(transpose_flip))
         wk = torch.empty((n,), device=weight.device, dtype=torch.float32)
         L.call('risp_conv_tc_prepare_weights', L.ptr(weight.detach().contiguous()), L.ptr(wk), Cin, Cout, K, int(transpose_flip), L.stream())
-        if cache is None or len(cache) > 8:
+        if cache is None or any(k[1:] != key[1:] for k in cache):
             cache = {}
         cache[key] = wk
         try:

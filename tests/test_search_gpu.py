@@ -74,3 +74,77 @@ def test_split_inference_matches_reference_blend():
     outs = [pipe.forward(torch.from_numpy(p).permute(2, 0, 1).unsqueeze(0))[0][0].permute(1, 2, 0).detach().numpy() for p in patches]
     merged = np.clip(O.patch2whole(np.array(outs), pos, cnt, (st, st)), 0, 1)
     assert float(np.abs(out.permute(1, 2, 0).cpu().numpy() - merged).max()) <= 1e-4
+
+
+def _opt_ft(n_step, ft_steps=1):
+    o = _opt(n_step)
+    o['model'] = 'darts_ft'
+    o['network_G']['which_model_G'] = 'SuperPruneFifteenDemosFourBayerTwoFt'
+    o['proxy_ft_params'] = {'memory_size': 4, 'ft_steps': ft_steps}
+    return o
+
+
+def test_proxy_finetune_step_matches_oracle():
+    """darts_ft_model.py:185-231: one fine-tune step per flagged proxy -- loss and weight/bias gradients against
+    the oracle's SRCNNRes + classical targets under autograd, with the reference's host RNG draws."""
+    import random
+    from reconfigisp_b200.networks import create_model
+    n_step = 2
+    m = create_model(_opt_ft(n_step))
+    assert [n for n, *_ in m.ft_nets] == ['crysisengine', 'whiteworld', 'bilateral', 'median']
+    g = torch.Generator().manual_seed(4)
+    mem = [torch.rand(2, 3, 24, 32, generator=g) * 0.9 + 0.05 for _ in range(3)]
+    m.ft_data = [t.cuda() for t in mem]
+    before = {n: [p.detach().clone() for p in proxy.parameters()] for n, proxy, *_ in m.ft_nets}
+    random.seed(3); torch.manual_seed(3)
+    m.finetune_proxies()
+    # oracle replay
+    random.seed(3); torch.manual_seed(3)
+    oS = PO.Supernet(n_step, 0.2, 10)
+    names = [n for n, _ in PO.SRGB_STEP]
+    for name, proxy, _, _ in m.ft_nets:
+        data = mem[int(random.random() * len(mem))]
+        param = torch.rand(1, oS.steps[-1][names.index(name)].P).repeat(data.shape[0], 1)
+        sd = {k: v.clone().requires_grad_() for k, v in oS.steps[-1][names.index(name)].sd.items()}
+        out = O.srcnn_res(data, param, sd)
+        gt = PO.ORIGIN[name](data, param)
+        loss = O.mse(out, gt)
+        keys = [k for k, _ in proxy.named_parameters()]
+        grads = torch.autograd.grad(loss, [sd[k] for k in keys])
+        assert abs(float(m.log_dict['ft_' + name]) - float(loss)) <= 2e-5 * max(1.0, float(loss)), name
+        for k, p, r in zip(keys, proxy.parameters(), grads):
+            relclose(p.grad, r, rtol=3e-3)
+        # Adam moved the weights, and load_proxy_nets copied them into every sRGB step
+        idx = names.index(name)
+        for p0, p1, p2 in zip(before[name], m.netG.all_modules[-1][idx].parameters(), m.netG.all_modules[-2][idx].parameters()):
+            assert float((p1 - p0).abs().max()) > 0
+            assert torch.equal(p1, p2)
+
+
+def test_proxy_finetune_reduces_proxy_error_and_search_continues():
+    """The online loop of train_ft.py: search iterations fill the FIFO, fine-tuning lowers the proxy-vs-original
+    error, and the tuned weights are the ones the next supernet forward uses."""
+    import random
+    from reconfigisp_b200.networks import create_model
+    from reconfigisp_b200 import ops
+    opt = _opt_ft(1, ft_steps=12)
+    opt['train']['lr_G'] = 1e-3
+    m = create_model(opt)
+    g = torch.Generator().manual_seed(6)
+    batch = lambda: (torch.rand(2, 1, 32, 32, generator=g) * 0.8 + 0.1, torch.rand(2, 3, 32, 32, generator=g),
+                     torch.rand(2, 1, 32, 32, generator=g) * 0.8 + 0.1, torch.rand(2, 3, 32, 32, generator=g))
+    for _ in range(3):
+        m.feed_data(batch()); m.optimize_alphas(); m.optimize_parameters()
+    assert 0 < len(m.ft_data) <= 4 and all(t.shape[1] == 3 for t in m.ft_data)
+    name, proxy, target, _ = m.ft_nets[0]
+    data, param = m.ft_data[-1], torch.full((2, 1), 0.5).cuda()
+    with torch.no_grad():
+        e0 = float(ops.mse_loss(proxy(data, param), target(data, param)))
+    random.seed(0); torch.manual_seed(0)
+    for _ in range(4):
+        m.finetune_proxies()
+    with torch.no_grad():
+        e1 = float(ops.mse_loss(proxy(data, param), target(data, param)))
+    assert e1 < e0, (e0, e1)
+    m.feed_data(batch()); m.optimize_alphas(); m.optimize_parameters()
+    assert torch.isfinite(m.log_dict['loss'])
