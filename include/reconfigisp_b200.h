@@ -169,6 +169,12 @@ int risp_kth_largest(const float* x, const long long* k, float* out, int planes,
  * guided filter / sharpening are north_star extensions).  Shared-memory halo tiles.
  * ------------------------------------------------------------------------------------- */
 /* window/sigma_color/sigma_space: DEVICE per-image arrays (window: int32, odd, <= 15) */
+/* spatialnoisereduction.run(img, 'fastnlm', {block_size, search_block: IntTensor(N,), decay_factor: Tensor(N,)})
+ * (tools_origin.py:785-797): non-local means as defined in oracle/SPEC.md -- s x s search window, b x b patches compared
+ * jointly over the 3 channels, w = exp(-mean_sq_diff / h^2), reflect-101 borders.  max_halo >= max_n(b/2 + s/2), <= 16. */
+int risp_fastnlm_fwd(const float* x, float* y, int N, int H, int W, const int* block_size, const int* search_block,
+                     const float* decay_factor, int max_halo, risp_stream_t stream);
+
 /* max_window: HOST upper bound of window[] (sizes the halo tile); larger device values are clamped */
 int risp_bilateral_fwd(const float* x, float* y, int N, int H, int W, const int* window,
                        const float* sigma_color, const float* sigma_space, int max_window,

@@ -266,6 +266,30 @@ def denoise_bilateral(x, window, sigma_color, sigma_space):
     return out
 
 
+def denoise_fastnlm(x, block_size, search_block, decay):
+    """UNPINNED (`tools_origin.py:785-797`; definition in SPEC.md).  (N,3,H,W) any range; per-image odd block /
+    search sizes, decay h on the data's scale.  Classic non-local means: weights exp(-d2/h^2) with d2 the mean
+    squared difference of the b x b patches over the 3 channels; reflect-101 borders."""
+    N, C, H, W = x.shape
+    out = torch.empty_like(x)
+    for n in range(N):
+        rb, rs = int(block_size[n]) // 2, int(search_block[n]) // 2
+        h = float(decay[n])
+        R = rb + rs
+        xp = F.pad(x[n:n + 1], (R,) * 4, mode='reflect') if R > 0 else x[n:n + 1]
+        num = torch.zeros_like(x[n]); den = torch.zeros_like(x[n, 0])
+        ctr = xp[:, :, rs: rs + H + 2 * rb, rs: rs + W + 2 * rb]
+        for dy in range(-rs, rs + 1):
+            for dx in range(-rs, rs + 1):
+                sh = xp[:, :, rs + dy: rs + dy + H + 2 * rb, rs + dx: rs + dx + W + 2 * rb]
+                d2 = F.avg_pool2d(((ctr - sh) ** 2).sum(dim=1, keepdim=True), 2 * rb + 1, stride=1)[0, 0] / 3.0
+                w = torch.exp(-d2 / (h * h))
+                num += w * xp[0, :, R + dy: R + dy + H, R + dx: R + dx + W]
+                den += w
+        out[n] = num / den
+    return out
+
+
 def denoise_median(x, size):
     """Per-channel k x k median, replicate borders (cv2.medianBlur semantics)."""
     rad = size // 2

@@ -89,6 +89,12 @@ def m_median(x, p):                                                             
     return O.denoise_median(x * 255., k).float() / 255.
 
 
+def m_fastnlm(x, p):                                                             # :762-804
+    p = p.detach()
+    blk, srch = O.bilateral_window_from_param(p[:, 0]), O.bilateral_window_from_param(p[:, 1])
+    return O.denoise_fastnlm(x * 255., blk, srch, p[:, 2] * 99 + 1).float() / 255.
+
+
 class Net:
     """A CNN candidate with its weights (tools_proxy.py)."""
     def __init__(self, arch, P, seed):
@@ -115,7 +121,7 @@ CLASSICAL = {'gamma': m_gamma, 'grayworld': m_grayworld, 'skip': m_skip, 'wbmanu
              'wbquadratic': m_wbquadratic, 'gtmmanual': m_gtmmanual, 'nearest': m_nearest,
              'demosaicnet': m_demosaicnet}
 ORIGIN = {'reinhard': m_reinhard, 'crysisengine': m_crysis, 'filmic': m_filmic, 'whiteworld': m_whiteworld,
-          'bilateral': m_bilateral, 'median': m_median, 'bilinear': m_bilinear, 'laplacian': m_laplacian}
+          'bilateral': m_bilateral, 'median': m_median, 'fastnlm': m_fastnlm, 'bilinear': m_bilinear, 'laplacian': m_laplacian}
 
 
 def parse_architecture(architecture):

@@ -86,7 +86,9 @@ class _SpatialNoiseReduction:
                                               params['sigma_space'])
         if option == 'median':
             return _nhwc(O.denoise_median)(img, params['size'])
-        raise NotImplementedError('fastnlm: not restated')
+        if option == 'fastnlm':
+            return _nhwc(O.denoise_fastnlm)(img, params['block_size'], params['search_block'], params['decay_factor'])
+        raise ValueError(option)
 
 
 def _install_kernel_stubs():

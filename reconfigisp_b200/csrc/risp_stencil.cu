@@ -72,6 +72,50 @@ bilateral_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int 
   o[0] = nb / den; o[plane] = ng / den; o[2 * plane] = nr / den;
 }
 
+// ---- non-local means (oracle/SPEC.md 'fastnlm') --------------------------------------------------------
+// y_c(p) = sum_q w(p,q) x_c(q) / sum_q w(p,q),  q over the s x s search window,
+// w = exp(-d2/h^2),  d2 = mean over the b x b patch and the 3 channels of (x(p+o) - x(q+o))^2.
+// Halo = s/2 + b/2 (reflect-101 applied while staging), everything runs out of the shared tile.
+__global__ void __launch_bounds__(kT)
+fastnlm_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, const int* __restrict__ block_size,
+               const int* __restrict__ search_block, const float* __restrict__ decay, int Rmax) {
+  extern __shared__ float sh[];
+  const int n = blockIdx.z;
+  int rb = block_size[n] / 2, rs = search_block[n] / 2;
+  rb = rb < 0 ? 0 : rb; rs = rs < 0 ? 0 : rs;
+  if (rb + rs > Rmax) { rs = rs > Rmax ? Rmax : rs; rb = Rmax - rs; }
+  const int R = rb + rs;
+  const float h = decay[n];
+  const float kexp = -1.f / (h * h * 3.f * (float)((2 * rb + 1) * (2 * rb + 1)));
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  const long long plane = (long long)H * W;
+  load_tile<3>(sh, x + (long long)n * 3 * plane, H, W, y0, x0, R, BORDER_REFLECT101, 1.f);
+  __syncthreads();
+  const int tx = threadIdx.x % TW, ty = threadIdx.x / TW;
+  const int gx = x0 + tx, gy = y0 + ty;
+  if (gx >= W || gy >= H) return;
+  const int tw = TW + 2 * R, ps = tw * (TH + 2 * R);
+  const float* c0 = sh + (ty + R) * tw + tx + R;
+  float nb = 0.f, ng = 0.f, nr = 0.f, den = 0.f;
+  for (int dy = -rs; dy <= rs; ++dy) {
+    for (int dx = -rs; dx <= rs; ++dx) {
+      const float* q0 = c0 + dy * tw + dx;
+      float d2 = 0.f;
+      for (int oy = -rb; oy <= rb; ++oy) {
+        for (int ox = -rb; ox <= rb; ++ox) {
+          const int o = oy * tw + ox;
+          const float eb = c0[o] - q0[o], eg = c0[o + ps] - q0[o + ps], er = c0[o + 2 * ps] - q0[o + 2 * ps];
+          d2 = fmaf(eb, eb, d2); d2 = fmaf(eg, eg, d2); d2 = fmaf(er, er, d2);
+        }
+      }
+      const float wgt = __expf(d2 * kexp);
+      nb = fmaf(wgt, q0[0], nb); ng = fmaf(wgt, q0[ps], ng); nr = fmaf(wgt, q0[2 * ps], nr); den += wgt;
+    }
+  }
+  float* o = y + (long long)n * 3 * plane + (long long)gy * W + gx;
+  o[0] = nb / den; o[plane] = ng / den; o[2 * plane] = nr / den;
+}
+
 // ---- median ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cswap(float& a, float& b) { float t = fminf(a, b); b = fmaxf(a, b); a = t; }
 
@@ -304,6 +348,18 @@ extern "C" int risp_bilateral_fwd(const float* x, float* y, int N, int H, int W,
   bilateral_kernel<<<tile_grid(H, W, N), kT, tile_smem(R, 3), as_stream(stream)>>>(x, y, H, W, window, sigma_color,
                                                                                 sigma_space, R);
   return check_launch("bilateral_kernel");
+}
+
+extern "C" int risp_fastnlm_fwd(const float* x, float* y, int N, int H, int W, const int* block_size,
+                                const int* search_block, const float* decay_factor, int max_halo, risp_stream_t stream) {
+  RISP_REQUIRE(x && y && block_size && search_block && decay_factor && N > 0 && H > 1 && W > 1, RISP_E_INVALID,
+               "risp_fastnlm_fwd: bad arguments");
+  RISP_REQUIRE(max_halo >= 0 && max_halo <= 2 * kMaxR, RISP_E_INVALID, "risp_fastnlm_fwd: max_halo %d not in [0,%d]", max_halo,
+               2 * kMaxR);
+  RISP_REQUIRE(N <= 65535, RISP_E_INVALID, "risp_fastnlm_fwd: batch too large");
+  fastnlm_kernel<<<tile_grid(H, W, N), kT, tile_smem(max_halo, 3), as_stream(stream)>>>(x, y, H, W, block_size, search_block,
+                                                                                     decay_factor, max_halo);
+  return check_launch("fastnlm_kernel");
 }
 
 extern "C" int risp_median_fwd(const float* x, float* y, int N, int H, int W, int size, risp_stream_t stream) {

@@ -3,7 +3,7 @@
     SpatialNoiseReduction().run(img_NHWC in [0,255], option, params) -> NHWC in [0,255]  (forward only)
       'bilateral'  window_length IntTensor (N,), sigma_color / sigma_space Tensor (N,)  (tools_origin.py:696-710)
       'median'     size int                                                              (:742-751)
-      'fastnlm'    not restated (only its SRCNNRes proxy is on the search path)
+      'fastnlm'    block_size / search_block IntTensor (N,), decay_factor Tensor (N,)        (:785-797; oracle/SPEC.md)
 """
 import torch
 
@@ -21,7 +21,8 @@ class SpatialNoiseReduction:
         elif option == 'median':
             y = ops.median(x, int(params['size']))
         elif option == 'fastnlm':
-            raise NotImplementedError('spatialnoisereduction: fastnlm is outside the rebuilt hot path')
+            as_int = lambda v: (v if torch.is_tensor(v) else torch.as_tensor(v)).reshape(-1)
+            y = ops.fastnlm(x, as_int(params['block_size']), as_int(params['search_block']), dev_vec(params['decay_factor'], x))
         else:
             raise ValueError('spatialnoisereduction: unknown option %r' % (option,))
         return nchw_to_nhwc(y)

@@ -251,7 +251,12 @@ class OriginNoiseMedian(nn.Module):
 
 
 class OriginNoiseFastnlm(nn.Module):
-    """tools_origin.py:762-804 -- not restated (outside the rebuilt hot path)."""
+    """tools_origin.py:762-804.  Same `.int()*7` quirk as the bilateral window (:786-787): block and search sizes
+    are 3 unless p == 1 (then 17); decay h = p*99+1 on the 0-255 scale (:788), applied to [0,1] data here."""
 
     def forward(self, img, params):
-        raise NotImplementedError('fastnlm is not part of the rebuilt hot path; use its SRCNNRes proxy')
+        p = params.detach()
+        block = (p[:, 0].int() * 7) * 2 + 3
+        search = (p[:, 1].int() * 7) * 2 + 3
+        h = (p[:, 2] * 99 + 1) / 255.0
+        return ops.fastnlm(img, block, search, h, max_halo=16)

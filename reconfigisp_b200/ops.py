@@ -362,6 +362,20 @@ def bilateral(x, window, sigma_color, sigma_space, max_window=None):
     return y
 
 
+def fastnlm(x, block_size, search_block, decay_factor, max_halo=None):
+    """Non-local means (oracle/SPEC.md); per-image odd block / search sizes and decay h."""
+    x = _img(x.detach(), 3)
+    N, _, H, W = x.shape
+    block_size = block_size.to(device=x.device, dtype=torch.int32).contiguous()
+    search_block = search_block.to(device=x.device, dtype=torch.int32).contiguous()
+    if max_halo is None:
+        max_halo = int((block_size // 2 + search_block // 2).max().item())
+    y = torch.empty_like(x)
+    L.call('risp_fastnlm_fwd', L.ptr(x), L.ptr(y), N, H, W, L.ptr(block_size), L.ptr(search_block),
+           L.ptr(decay_factor.to(x.device).float().contiguous()), int(max_halo), L.stream())
+    return y
+
+
 def median(x, size):
     x = _img(x.detach(), 3)
     N, _, H, W = x.shape

@@ -1,16 +1,14 @@
 """`DartsFtModel` -- DARTS search with ONLINE PROXY FINE-TUNING (codes/models/darts_ft_model.py:20-368,
 driven by codes/train_ft.py): the search loop of `DartsModel`, plus a FIFO memory of the sRGB intermediates
 the supernet produced, and every `ft_interval` iterations a few Adam steps that pull each flagged proxy CNN
-(crysisengine / whiteworld / bilateral / median) back towards its classical original on those intermediates
+(crysisengine / whiteworld / bilateral / median / fastnlm) back towards its classical original on those intermediates
 with random parameters; the tuned weights are then copied into every sRGB step of the supernet.
 
 What it runs on: proxy forward / data gradient = tcgen05 convolution, weight gradient = `risp_conv2d_bwd_weight`,
 targets = the classical CUDA ops (`Origin*`).  B200 changes: the FIFO stays in HBM (the reference moves every
 intermediate to the host and back, :174-175/:199); proxy gradients of all ranks are averaged in one flattened
 all-reduce (the reference wraps each proxy in DDP, :83-85).
-
-`fastnlm` is flagged upstream (:113 of the supernet file) but its target is OpenCV's fastNlMeansDenoisingColored,
-which is outside the rebuilt path: it is skipped with a warning and keeps its loaded weights."""
+"""
 import logging
 import random
 
@@ -34,7 +32,8 @@ class DartsFtModel(DartsModel):
         self.ft_data = []
         t = opt['train']
         targets = {'reinhard': TO.OriginToneReinhard, 'crysisengine': TO.OriginToneCrysis, 'filmic': TO.OriginToneFilmic,
-                   'whiteworld': TO.OriginWbWhiteworld, 'bilateral': TO.OriginNoiseBilateral, 'median': TO.OriginNoiseMedian}
+                   'whiteworld': TO.OriginWbWhiteworld, 'bilateral': TO.OriginNoiseBilateral, 'median': TO.OriginNoiseMedian,
+                   'fastnlm': TO.OriginNoiseFastnlm}
         self.ft_nets = []          # [name, proxy, target, optimizer]; the proxy is the LAST step's instance (:79)
         for (name, flag), proxy in zip(self.netG.proxy_ft_flag, self.netG.all_modules[-1]):
             if not flag:

@@ -63,7 +63,8 @@ def test_cnn_candidates_match_reference(golden):
 
 
 ARCHS = (('classical', 'Bayer_02_Demosaic_02_sRGB_11_13_01'), ('sid', 'Bayer_01_Demosaic_03_sRGB_01_13_11'),
-         ('s7isp', 'Bayer_01_Demosaic_01_sRGB_04_01_13'), ('all_origin', 'Bayer_02_Demosaic_01_sRGB_05_02_03_04_06_07_08_10_12_15'))
+         ('s7isp', 'Bayer_01_Demosaic_01_sRGB_04_01_13'), ('all_origin', 'Bayer_02_Demosaic_01_sRGB_05_02_03_04_06_07_08_10_12_15'),
+         ('nlm', 'Bayer_02_Demosaic_01_sRGB_09_01'))
 
 
 @pytest.mark.parametrize('fuse', [False, True])
@@ -200,5 +201,8 @@ def test_plugin_boundary_run_signatures():
     out = spatialnoisereduction.SpatialNoiseReduction().run(nhwc * 255., 'bilateral', {
         'window_length': win.cuda(), 'sigma_color': torch.tensor([20., 50.]).cuda(), 'sigma_space': torch.tensor([5., 2.]).cuda()})
     assert maxabs(out.permute(0, 3, 1, 2) / 255, O.denoise_bilateral(x * 255, win, [20., 50.], [5., 2.]) / 255) <= 1e-4
+    out = spatialnoisereduction.SpatialNoiseReduction().run(nhwc * 255., 'fastnlm', {
+        'block_size': win.cuda(), 'search_block': torch.tensor([5, 3], dtype=torch.int32).cuda(), 'decay_factor': torch.tensor([20., 50.]).cuda()})
+    assert maxabs(out.permute(0, 3, 1, 2) / 255, O.denoise_fastnlm(x * 255, win, [5, 3], [20., 50.]) / 255) <= 1e-4
     with pytest.raises(ValueError):
         gamma.Gamma().run(nhwc, 'auto', {})

@@ -279,6 +279,11 @@ def test_stencils(ops):
     yb = ops.bilateral(dev(x255), dev(win), dev(sc), dev(ss))
     assert maxabs(yb / 255, O.denoise_bilateral(x255, win, sc, ss) / 255) <= TOL
     assert maxabs(ops.guided_filter(dev(x), 2, 1e-2), O.guided_filter(x, 2, 1e-2)) <= TOL
+    # non-local means: per-image sizes, small and large decay, and the p == 1 corner of the wrapper (17 / 17)
+    for blk, srch, h in (([3, 3], [3, 3], [12., 60.]), ([5, 3], [7, 9], [25., 8.]), ([17, 1], [17, 5], [40., 3.])):
+        blk, srch, h = torch.tensor(blk, dtype=torch.int32), torch.tensor(srch, dtype=torch.int32), torch.tensor(h)
+        yn = ops.fastnlm(dev(x255), dev(blk), dev(srch), dev(h))
+        assert maxabs(yn / 255, O.denoise_fastnlm(x255, blk, srch, h) / 255) <= TOL, (blk, srch)
     a = torch.tensor([[0.7], [1.5]])
     xo, ao = x.clone().requires_grad_(), a.clone().requires_grad_()
     yo = O.sharpen(xo, ao)

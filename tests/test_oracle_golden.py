@@ -99,7 +99,8 @@ def test_fixed_pipelines(golden):
     raw = T(g['raw'])
     for tag, arch in (('classical', 'Bayer_02_Demosaic_02_sRGB_11_13_01'), ('sid', 'Bayer_01_Demosaic_03_sRGB_01_13_11'),
                       ('s7isp', 'Bayer_01_Demosaic_01_sRGB_04_01_13'),
-                      ('all_origin', 'Bayer_02_Demosaic_01_sRGB_05_02_03_04_06_07_08_10_12_15')):
+                      ('all_origin', 'Bayer_02_Demosaic_01_sRGB_05_02_03_04_06_07_08_10_12_15'),
+         ('nlm', 'Bayer_02_Demosaic_01_sRGB_09_01')):
         pipe = PO.FixedPipeline(arch, 'origin', 10)
         y, inter = pipe.forward(raw)
         close(y, g[tag + '_y'], 2e-6)

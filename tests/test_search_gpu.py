@@ -91,7 +91,7 @@ def test_proxy_finetune_step_matches_oracle():
     from reconfigisp_b200.networks import create_model
     n_step = 2
     m = create_model(_opt_ft(n_step))
-    assert [n for n, *_ in m.ft_nets] == ['crysisengine', 'whiteworld', 'bilateral', 'median']
+    assert [n for n, *_ in m.ft_nets] == ['crysisengine', 'whiteworld', 'bilateral', 'median', 'fastnlm']
     g = torch.Generator().manual_seed(4)
     mem = [torch.rand(2, 3, 24, 32, generator=g) * 0.9 + 0.05 for _ in range(3)]
     m.ft_data = [t.cuda() for t in mem]
