@@ -113,8 +113,12 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
-    sample = (1504, 2000)
-    # a "step" = one fwd+bwd of the CPU port on the bounded sample
+    # a "step" = one fwd+bwd of the CPU port on a bounded sample of the workload (a crop of one 12 MP frame), sized
+    # from a probe so that the whole --steps/--warmup run stays within ~2 minutes
+    _, _, probe_dt = cpu_reference_rate((752, 1000), 1)
+    n = max(1, args.steps + args.warmup)
+    scale = min(4.0, max(0.25, (120.0 / n) / max(probe_dt, 1e-3)))         # pixels relative to the probe crop
+    sample = (int(752 * scale ** 0.5) // 2 * 2, int(1000 * scale ** 0.5) // 4 * 4)
     rate, cores, dt = cpu_reference_rate(sample, max(1, args.steps + args.warmup - 1))
     line = {'impl': 'reference', 'metric': METRIC, 'value': round(rate, 3), 'unit': 'MP/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(dt * 1e3, 2), 'higher_is_better': True,
@@ -171,7 +175,6 @@ def run_b200(args):
     sampler = ClockSampler(local)
     sampler.start()
     ms_total = timed(model.optimize_parameters, args.steps, args.warmup)
-    clocks = sampler.summary()
     ms_step = ms_total / args.steps
     value = world * px_per_step_rank / 1e6 / (ms_step / 1e3)
 
@@ -180,7 +183,8 @@ def run_b200(args):
         model.feed_data((raw_h, gt_h))
         model.optimize_parameters()
         return float(model.log_dict['loss'].item())
-    ms_e2e = timed(e2e_step, max(2, min(args.steps, 10)), 2) / max(2, min(args.steps, 10))
+    n_e2e = max(2, min(args.steps, 40))
+    ms_e2e = timed(e2e_step, n_e2e, 3) / n_e2e
     e2e = world * px_per_step_rank / 1e6 / (ms_e2e / 1e3)
 
     # ---- e2e with the device-side codec: the loaders' integer codes cross PCIe, /1023 and /255 happen on the GPU --
@@ -191,7 +195,7 @@ def run_b200(args):
         model.feed_data((raw_c, gt_c))
         model.optimize_parameters()
         return float(model.log_dict['loss'].item())
-    ms_codec = timed(e2e_codec_step, max(2, min(args.steps, 10)), 2) / max(2, min(args.steps, 10))
+    ms_codec = timed(e2e_codec_step, n_e2e, 3) / n_e2e
     e2e_codec = world * px_per_step_rank / 1e6 / (ms_codec / 1e3)
 
     # ---- roofline of the dominant kernel ----------------------------------------------------------------------
@@ -200,6 +204,7 @@ def run_b200(args):
     with torch.no_grad():
         table = model.netG._segment_table(keep, B).contiguous()
     ms_k = timed(lambda: step(model.img, model.gt, table), args.steps, args.warmup) / args.steps
+    clocks = sampler.summary()          # sampled across all timed legs (value, e2e, e2e_codec, roofline)
     peak, peak_src = measured_peak_gbs()
     achieved = ALGO_BYTES_PER_PX * px_per_step_rank / (ms_k / 1e3) / 1e9
 
@@ -230,9 +235,10 @@ def run_b200(args):
             except Exception:
                 pass
     if rank == 0 and world == 1 and not args.no_cpu:
-        rate, cores, dt = cpu_reference_rate((1504, 2000), 2)
+        rate, cores, dt = cpu_reference_rate((H, W), 8)
         line['cpu_baseline'] = {'value': round(rate, 3), 'unit': 'MP/s', 'cores': cores, 'kind': 'port',
-                                'sample': '1 frame 1504x2000, 2 reps of fwd+bwd (oracle/pipeline_oracle.py, torch CPU)'}
+                                'sample': '1 frame %dx%d of the workload, 1 warm-up + 8 reps of fwd+bwd = %.1f s '
+                                          '(oracle/pipeline_oracle.py FixedPipeline, torch CPU)' % (H, W, 9 * dt)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -244,7 +250,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--frames', type=int, default=FRAMES_PER_GPU, help='12MP frames per GPU per step')

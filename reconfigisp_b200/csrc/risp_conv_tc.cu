@@ -92,14 +92,23 @@ __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float (&v)[16]) {
 }
 
 // ---- kernel ---------------------------------------------------------------------------------------------
-// K: filter size; CI_C: input channels per chunk (multiple of 8); R: output rows per CTA; NP: padded Cout (16/32/48/64)
+// K: filter size; CI_C: input channels per chunk (multiple of 8); R: output rows per CTA; NP: padded Cout (16/32/48/64);
+// TPS: filter taps per weight stage (divides K*K)
 //
 // Accuracy note (measured on B200): every tcgen05.mma rounds its fp32 accumulator once, toward zero, so the error
 // of one accumulator grows linearly with the number of MMAs chained into it (~6e-8 relative each).  The two
 // cross terms (a_lo*b_hi, a_hi*b_lo) are ~2^-11 of the main term, so they get their OWN accumulator: the main
 // accumulator then sees one rounding per 8 input channels per tap instead of three, and the roundings of the
 // small accumulator are 2^-11 times less significant.  The two accumulators are added in the epilogue.
-template <int K, int CI_C, int R, int NP, int DYB>
+//
+// Pipeline of one CTA (two CTAs are resident per SM and fill each other's gaps):
+//   weights  : double-buffered stages of TPS taps, fetched by 1-D bulk async copies (TMA engine, no registers, no
+//              thread work) that signal bfull[buf] by complete_tx; the issuing lane refills a buffer as soon as the
+//              MMAs that read it have committed (mdone[buf])
+//   inputs   : the rows of the NEXT input-channel chunk are loaded into registers while the MMAs of the current
+//              chunk run, and only split (hi/lo) + stored once those MMAs have committed (afree, one phase per chunk)
+//   MMAs     : one elected lane of warp 0
+template <int K, int CI_C, int R, int NP, int TPS>
 struct TcCfg {
   static constexpr int PAD = K / 2;
   static constexpr int PW = TC_M + K - 1;                 // staged pixels per row
@@ -108,26 +117,37 @@ struct TcCfg {
   static constexpr int A_ROW_FLOATS = KG * PW * 4;        // one staged row, one precision
   static constexpr int A_FLOATS = ROWS * A_ROW_FLOATS;    // hi (lo follows)
   static constexpr int B_TAP_FLOATS = KG * NP * 4;        // one tap, one precision
-  static constexpr int B_FLOATS = DYB * K * B_TAP_FLOATS; // DYB tap rows of one chunk (hi), lo follows
+  static constexpr int B_STAGE_FLOATS = TPS * B_TAP_FLOATS;
   static constexpr int B_CHUNK_FLOATS = K * K * B_TAP_FLOATS;
-  static_assert(K % DYB == 0, "tap rows per stage must divide K");
-  static constexpr size_t SMEM = sizeof(float) * (2 * A_FLOATS + 2 * B_FLOATS) + 64;
+  static constexpr int NST = K * K / TPS;                 // weight stages per chunk
+  static_assert((K * K) % TPS == 0, "taps per stage must divide K*K");
+  static constexpr size_t SMEM = sizeof(float) * (2 * A_FLOATS + 4 * B_STAGE_FLOATS) + 64;
   static constexpr int ACC_COLS = 2 * R * NP;             // main + cross-term accumulators
   static constexpr int TMEM_COLS = (ACC_COLS <= 32) ? 32 : (ACC_COLS <= 64) ? 64 : (ACC_COLS <= 128) ? 128 : (ACC_COLS <= 256) ? 256 : 512;
   static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
+  static constexpr int A_TOTAL = ROWS * KG * PW;          // float4 elements staged per chunk
+  static constexpr int A_ITER = (A_TOTAL + TC_THREADS - 1) / TC_THREADS;
 };
 
-template <int K, int CI_C, int R, int NP, int DYB>
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+
+template <int K, int CI_C, int R, int NP, int TPS>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 conv_tc_kernel(ConvTcArgs a) {
-  using C = TcCfg<K, CI_C, R, NP, DYB>;
+  using C = TcCfg<K, CI_C, R, NP, TPS>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* sA_hi = reinterpret_cast<float*>(smem_raw);
   float* sA_lo = sA_hi + C::A_FLOATS;
-  float* sB_hi = sA_lo + C::A_FLOATS;
-  float* sB_lo = sB_hi + C::B_FLOATS;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(sB_lo + C::B_FLOATS);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  float* sB = sA_lo + C::A_FLOATS;                         // [buf][hi|lo][B_STAGE_FLOATS]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sB + 4 * C::B_STAGE_FLOATS);   // bfull[2], mdone[2], afree
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 5);
+  const uint32_t bfull = smem_u32(mbar), mdone = smem_u32(mbar + 2), afree = smem_u32(mbar + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int strips = (a.W + TC_M - 1) / TC_M;
@@ -140,7 +160,10 @@ conv_tc_kernel(ConvTcArgs a) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (tid == 0) mbar_init(smem_u32(mbar), 1);
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) mbar_init(smem_u32(mbar + i), 1);
+  }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   tc_fence_before();
   __syncthreads();
@@ -150,118 +173,127 @@ conv_tc_kernel(ConvTcArgs a) {
   constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
   const int n_chunks = (a.CinG * 4 + CI_C - 1) / CI_C;
+  const int n_stages = n_chunks * C::NST;
   const long long row_stride = (long long)a.CinG * a.W * 4;              // floats per image row (blocked layout)
   const float* xin = a.x + (long long)n * a.H * row_stride;
   const float* min_ = a.mask_in ? a.mask_in + (long long)n * a.H * row_stride : nullptr;
   const long long lo_off = (long long)n_chunks * C::B_CHUNK_FLOATS;
-  uint32_t phase = 0;
-  bool pending = false;      // a committed batch of MMAs may still be reading shared memory
+  constexpr uint32_t kStageBytes = C::B_STAGE_FLOATS * 4;
 
-  for (int c = 0; c < n_chunks; ++c) {
-    // the previous batch of MMAs still reads shared memory: wait for its commit before restaging
-    if (pending) { mbar_wait(smem_u32(mbar), phase); phase ^= 1; pending = false; }
-    __syncthreads();
-    // ---- stage the input rows of this chunk (hi / lo split, zero padding, optional input ReLU / mask) ----
-    // all global loads of the phase are issued first (ITER independent 128-bit loads per thread), then split and
-    // stored: otherwise every thread pays the L2 latency once per element it stages
-    {
-      constexpr int TOTAL = C::ROWS * C::KG * C::PW;
-      constexpr int ITER = (TOTAL + TC_THREADS - 1) / TC_THREADS;
-      float4 v[ITER], m[ITER];
+  // weight stage s -> buffer s&1 (hi block then lo block); issued by the MMA lane only
+  auto fetch_weights = [&](int s) {
+    const int c = s / C::NST, st = s % C::NST;
+    const long long off = (long long)c * C::B_CHUNK_FLOATS + (long long)st * C::B_STAGE_FLOATS;
+    const uint32_t bar = bfull + 8u * (uint32_t)(s & 1);
+    const uint32_t dst = smem_u32(sB) + (uint32_t)(s & 1) * 2u * kStageBytes;
+    mbar_expect_tx(bar, 2u * kStageBytes);
+    bulk_g2s(dst, a.wprep + off, kStageBytes, bar);
+    bulk_g2s(dst + kStageBytes, a.wprep + lo_off + off, kStageBytes, bar);
+  };
+
+  // input rows of chunk c -> registers (zero padding, optional mask / ReLU applied here so only one array stays live)
+  float4 v[C::A_ITER];
+  auto load_inputs = [&](int c) {
 #pragma unroll
-      for (int it = 0; it < ITER; ++it) {
-        const int i = tid + it * TC_THREADS;
-        const int px = i % C::PW;
-        const int kg = (i / C::PW) % C::KG;
-        const int row = i / (C::PW * C::KG);
-        const int gy = y0 - C::PAD + row, gx = x0 - C::PAD + px, gkg = c * C::KG + kg;
-        v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        m[it] = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (i < TOTAL && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && gkg < a.CinG) {
-          const long long o = (long long)gy * row_stride + ((long long)gkg * a.W + gx) * 4;
-          v[it] = __ldg(reinterpret_cast<const float4*>(xin + o));
-          if (min_) m[it] = __ldg(reinterpret_cast<const float4*>(min_ + o));
+    for (int it = 0; it < C::A_ITER; ++it) {
+      const int i = tid + it * TC_THREADS;
+      const int px = i % C::PW;
+      const int kg = (i / C::PW) % C::KG;
+      const int row = i / (C::PW * C::KG);
+      const int gy = y0 - C::PAD + row, gx = x0 - C::PAD + px, gkg = c * C::KG + kg;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < C::A_TOTAL && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && gkg < a.CinG) {
+        const long long o = (long long)gy * row_stride + ((long long)gkg * a.W + gx) * 4;
+        t = __ldg(reinterpret_cast<const float4*>(xin + o));
+        if (min_) {
+          const float4 m = __ldg(reinterpret_cast<const float4*>(min_ + o));
+          t.x = m.x > 0.f ? t.x : 0.f; t.y = m.y > 0.f ? t.y : 0.f; t.z = m.z > 0.f ? t.z : 0.f; t.w = m.w > 0.f ? t.w : 0.f;
         }
       }
+      v[it] = t;
+    }
+  };
+  auto store_inputs = [&]() {
 #pragma unroll
-      for (int it = 0; it < ITER; ++it) {
-        const int i = tid + it * TC_THREADS;
-        float4 t = v[it];
-        if (min_) { t.x = m[it].x > 0.f ? t.x : 0.f; t.y = m[it].y > 0.f ? t.y : 0.f; t.z = m[it].z > 0.f ? t.z : 0.f; t.w = m[it].w > 0.f ? t.w : 0.f; }
-        if (relu_in) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
-        float4 hi, lo;
-        hi.x = __uint_as_float(__float_as_uint(t.x) & 0xffffe000u); lo.x = t.x - hi.x;
-        hi.y = __uint_as_float(__float_as_uint(t.y) & 0xffffe000u); lo.y = t.y - hi.y;
-        hi.z = __uint_as_float(__float_as_uint(t.z) & 0xffffe000u); lo.z = t.z - hi.z;
-        hi.w = __uint_as_float(__float_as_uint(t.w) & 0xffffe000u); lo.w = t.w - hi.w;
-        if (i < TOTAL) {
-          reinterpret_cast<float4*>(sA_hi)[i] = hi;
-          reinterpret_cast<float4*>(sA_lo)[i] = lo;
-        }
+    for (int it = 0; it < C::A_ITER; ++it) {
+      const int i = tid + it * TC_THREADS;
+      float4 t = v[it];
+      if (relu_in) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+      float4 hi, lo;
+      hi.x = __uint_as_float(__float_as_uint(t.x) & 0xffffe000u); lo.x = t.x - hi.x;
+      hi.y = __uint_as_float(__float_as_uint(t.y) & 0xffffe000u); lo.y = t.y - hi.y;
+      hi.z = __uint_as_float(__float_as_uint(t.z) & 0xffffe000u); lo.z = t.z - hi.z;
+      hi.w = __uint_as_float(__float_as_uint(t.w) & 0xffffe000u); lo.w = t.w - hi.w;
+      if (i < C::A_TOTAL) {
+        reinterpret_cast<float4*>(sA_hi)[i] = hi;
+        reinterpret_cast<float4*>(sA_lo)[i] = lo;
       }
     }
-    for (int dy0 = 0; dy0 < K; dy0 += DYB) {
-      // ---- stage DYB tap rows of this chunk's weights (hi and lo blocks are contiguous in wprep) ----
-      if (pending) { mbar_wait(smem_u32(mbar), phase); phase ^= 1; pending = false; }
-      {
-        const long long off = (long long)c * C::B_CHUNK_FLOATS + (long long)dy0 * K * C::B_TAP_FLOATS;
-        const float4* gh = reinterpret_cast<const float4*>(a.wprep + off);
-        const float4* gl = reinterpret_cast<const float4*>(a.wprep + lo_off + off);
-        constexpr int BTOT = C::B_FLOATS / 4;
-        constexpr int BITER = (BTOT + TC_THREADS - 1) / TC_THREADS;
-        float4 bh[BITER], bl[BITER];
-#pragma unroll
-        for (int it = 0; it < BITER; ++it) {
-          const int i = tid + it * TC_THREADS;
-          if (i < BTOT) { bh[it] = __ldg(gh + i); bl[it] = __ldg(gl + i); }
-        }
-#pragma unroll
-        for (int it = 0; it < BITER; ++it) {
-          const int i = tid + it * TC_THREADS;
-          if (i < BTOT) { reinterpret_cast<float4*>(sB_hi)[i] = bh[it]; reinterpret_cast<float4*>(sB_lo)[i] = bl[it]; }
-        }
-      }
-      fence_async_smem();      // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+  };
+
+  // ---- prologue: weights of stage 0 in flight, inputs of chunk 0 staged ----
+  if (warp == 0) {
+    if (elect_one()) fetch_weights(0);
+    __syncwarp();
+  }
+  load_inputs(0);
+  store_inputs();
+  fence_async_smem();        // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+  tc_fence_before();
+  __syncthreads();
+
+  for (int s = 0; s < n_stages; ++s) {
+    const int c = s / C::NST, st = s % C::NST;
+    if (st == 0 && s > 0) {
+      // chunk boundary: the MMAs of chunk c-1 (the only readers of the input tile) must have committed
+      mbar_wait(afree, (uint32_t)((c - 1) & 1));
+      store_inputs();          // registers were loaded while those MMAs ran
+      fence_async_smem();
       tc_fence_before();
       __syncthreads();
-      if (warp == 0) {
-       if (elect_one()) {
+    }
+    if (warp == 0) {
+      if (elect_one()) {
+        mbar_wait(bfull + 8u * (uint32_t)(s & 1), (uint32_t)((s >> 1) & 1));
         tc_fence_after();
+        const uint32_t sBh = smem_u32(sB) + (uint32_t)(s & 1) * 2u * kStageBytes, sBl = sBh + kStageBytes;
 #pragma unroll 1
-        for (int dyl = 0; dyl < DYB; ++dyl) {
-          const int dy = dy0 + dyl;
+        for (int tl = 0; tl < TPS; ++tl) {
+          const int tap = st * TPS + tl;
+          const int dy = tap / K, dx = tap % K;
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             const uint32_t d_main = tmem_base + (uint32_t)(r * NP);
             const uint32_t d_cross = tmem_base + (uint32_t)((R + r) * NP);
-            const uint32_t a_row = (uint32_t)((r + dy) * C::A_ROW_FLOATS * 4);
 #pragma unroll
-            for (int dx = 0; dx < K; ++dx) {
-#pragma unroll
-              for (int ks = 0; ks < C::KG / 2; ++ks) {
-                const uint32_t a_off = a_row + (uint32_t)((2 * ks) * C::PW * 16 + dx * 16);
-                const uint32_t b_off = (uint32_t)(((dyl * K + dx) * C::KG + 2 * ks) * NP * 16);
-                const uint64_t dAh = make_desc(smem_u32(sA_hi) + a_off, C::PW * 16, 128);
-                const uint64_t dAl = make_desc(smem_u32(sA_lo) + a_off, C::PW * 16, 128);
-                const uint64_t dBh = make_desc(smem_u32(sB_hi) + b_off, NP * 16, 128);
-                const uint64_t dBl = make_desc(smem_u32(sB_lo) + b_off, NP * 16, 128);
-                const uint32_t acc = (c == 0 && dy == 0 && dx == 0 && ks == 0) ? 0u : 1u;
-                umma_tf32(d_main, dAh, dBh, idesc, acc);
-                umma_tf32(d_cross, dAl, dBh, idesc, acc);
-                umma_tf32(d_cross, dAh, dBl, idesc, 1u);
-              }
+            for (int ks = 0; ks < C::KG / 2; ++ks) {
+              const uint32_t a_off = (uint32_t)((r + dy) * C::A_ROW_FLOATS * 4 + (2 * ks) * C::PW * 16 + dx * 16);
+              const uint32_t b_off = (uint32_t)((tl * C::KG + 2 * ks) * NP * 16);
+              const uint64_t dAh = make_desc(smem_u32(sA_hi) + a_off, C::PW * 16, 128);
+              const uint64_t dAl = make_desc(smem_u32(sA_lo) + a_off, C::PW * 16, 128);
+              const uint64_t dBh = make_desc(sBh + b_off, NP * 16, 128);
+              const uint64_t dBl = make_desc(sBl + b_off, NP * 16, 128);
+              const uint32_t acc = (s == 0 && tl == 0 && ks == 0) ? 0u : 1u;
+              umma_tf32(d_main, dAh, dBh, idesc, acc);
+              umma_tf32(d_cross, dAl, dBh, idesc, acc);
+              umma_tf32(d_cross, dAh, dBl, idesc, 1u);
             }
           }
         }
-        umma_commit(smem_u32(mbar));
-       }
-       __syncwarp();
+        umma_commit(mdone + 8u * (uint32_t)(s & 1));
+        if (st == C::NST - 1) umma_commit(afree);            // one phase per chunk (and the last one gates the epilogue)
+        if (s + 1 < n_stages) {
+          // the other weight buffer was last read by stage s-1
+          if (s >= 1) mbar_wait(mdone + 8u * (uint32_t)((s + 1) & 1), (uint32_t)(((s - 1) >> 1) & 1));
+          fetch_weights(s + 1);
+        }
       }
-      pending = true;
+      __syncwarp();
     }
+    if (st == C::NST - 1 && c + 1 < n_chunks) load_inputs(c + 1);   // in flight while this chunk's MMAs run
   }
   // ---- epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).., and the (w/4)-th half of the 16-column groups ----
-  mbar_wait(smem_u32(mbar), phase);
+  mbar_wait(afree, (uint32_t)((n_chunks - 1) & 1));
   tc_fence_after();
   const bool relu_out = (a.flags & RISP_CONV_RELU_OUT) != 0, add_res = (a.flags & RISP_CONV_ADD_RES) != 0,
              res_relu = (a.flags & RISP_CONV_RES_RELU) != 0;
@@ -381,19 +413,19 @@ __global__ void from_blocked_kernel(const float* __restrict__ src, float* __rest
   }
 }
 
-template <int K, int CI_C, int R, int NP, int DYB>
+template <int K, int CI_C, int R, int NP, int TPS>
 static int launch_tc(const ConvTcArgs& a, int N, cudaStream_t st) {
-  using C = TcCfg<K, CI_C, R, NP, DYB>;
+  using C = TcCfg<K, CI_C, R, NP, TPS>;
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(conv_tc_kernel<K, CI_C, R, NP, DYB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_tc_kernel<K, CI_C, R, NP, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess) {
       set_error("conv_tc: cannot opt in to %zu bytes of shared memory", C::SMEM);
       return RISP_E_CUDA;
     }
     attr = true;
   }
   dim3 grid((unsigned)(cdiv(a.W, TC_M) * cdiv(a.H, R)), (unsigned)N);
-  conv_tc_kernel<K, CI_C, R, NP, DYB><<<grid, TC_THREADS, C::SMEM, st>>>(a);
+  conv_tc_kernel<K, CI_C, R, NP, TPS><<<grid, TC_THREADS, C::SMEM, st>>>(a);
   return check_launch("conv_tc_kernel");
 }
 
@@ -452,18 +484,18 @@ extern "C" int risp_conv_tc_fwd(const float* x_blk, const float* mask_in_blk, co
   const int NP = (Cout + 15) / 16 * 16;
   ConvTcArgs a{x_blk, wprep, bias, res_blk, mask_in_blk, mask_out_blk, y_blk, y_planar, risp_conv_tc_padded_channels(Cin) / 4, Cout, NP, H, W, flags};
   cudaStream_t st = as_stream(stream);
-#define RISP_TC(KK, RR, NN, DD) return launch_tc<KK, 8, RR, NN, DD>(a, N, st)
-  // rows per CTA: 2*R*NP TMEM columns <= 256 and shared memory <= ~100 KB so that two CTAs are resident per SM
-  // (one stages while the other multiplies); DYB = tap rows of weights staged per batch of MMAs
+#define RISP_TC(KK, RR, NN, TT) return launch_tc<KK, 8, RR, NN, TT>(a, N, st)
+  // rows per CTA: 2*R*NP TMEM columns <= 256 and shared memory <= ~112 KB so that two CTAs are resident per SM;
+  // TT = filter taps per (double-buffered) weight stage
   switch (K) {
     case 1:
       switch (NP) { case 16: RISP_TC(1, 8, 16, 1); case 32: RISP_TC(1, 4, 32, 1); case 48: RISP_TC(1, 2, 48, 1); default: RISP_TC(1, 2, 64, 1); }
     case 3:
-      switch (NP) { case 16: RISP_TC(3, 8, 16, 3); case 32: RISP_TC(3, 4, 32, 3); case 48: RISP_TC(3, 2, 48, 3); default: RISP_TC(3, 2, 64, 3); }
+      switch (NP) { case 16: RISP_TC(3, 8, 16, 9); case 32: RISP_TC(3, 4, 32, 9); case 48: RISP_TC(3, 2, 48, 9); default: RISP_TC(3, 2, 64, 9); }
     case 5:
-      switch (NP) { case 16: RISP_TC(5, 4, 16, 5); case 32: RISP_TC(5, 4, 32, 1); case 48: RISP_TC(5, 2, 48, 1); default: RISP_TC(5, 2, 64, 1); }
+      switch (NP) { case 16: RISP_TC(5, 4, 16, 5); case 32: RISP_TC(5, 4, 32, 5); case 48: RISP_TC(5, 2, 48, 5); default: RISP_TC(5, 2, 64, 5); }
     default:
-      switch (NP) { case 16: RISP_TC(9, 2, 16, 3); case 32: RISP_TC(9, 2, 32, 1); case 48: RISP_TC(9, 2, 48, 1); default: RISP_TC(9, 2, 64, 1); }
+      switch (NP) { case 16: RISP_TC(9, 2, 16, 9); case 32: RISP_TC(9, 2, 32, 3); case 48: RISP_TC(9, 2, 48, 3); default: RISP_TC(9, 2, 64, 3); }
   }
 #undef RISP_TC
 }
@@ -471,13 +503,13 @@ extern "C" int risp_conv_tc_fwd(const float* x_blk, const float* mask_in_blk, co
 // ---- micro-benchmark: raw tcgen05 tf32 issue / execution rate for the operand layout used above ---------------
 namespace risp {
 template <int NP>
-__global__ void __launch_bounds__(128, 1) mma_rate_kernel(long long* out, int iters, int n_acc, int split3) {
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(long long* out, int iters, int n_acc, int split3, int a_pw) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* sA = reinterpret_cast<float*>(smem_raw);          // 2 kgroups x 136 px x 4
-  float* sB = sA + 2 * 136 * 4 * 2;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(sB + 2 * NP * 4 * 2);
+  float* sA = reinterpret_cast<float*>(smem_raw);          // 2 precisions x 2 kgroups x a_pw px x 4
+  float* sB = sA + 2 * 2 * 160 * 4;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sB + 2 * 2 * NP * 4);
   uint32_t* slot = reinterpret_cast<uint32_t*>(mbar + 1);
-  for (int i = threadIdx.x; i < 2 * 136 * 4 * 2 + 2 * NP * 4 * 2; i += 128) sA[i] = 0.001f * (i & 63);
+  for (int i = threadIdx.x; i < 2 * 2 * 160 * 4 + 2 * 2 * NP * 4; i += 128) sA[i] = 0.001f * (i & 63);
   if (threadIdx.x < 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -490,23 +522,29 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(long long* out, int it
   tc_fence_after();
   const uint32_t tb = *slot;
   constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  if (threadIdx.x == 0) {
-    const uint64_t dA = make_desc(smem_u32(sA), 136 * 16, 128), dA2 = make_desc(smem_u32(sA + 2 * 136 * 4), 136 * 16, 128);
-    const uint64_t dB = make_desc(smem_u32(sB), NP * 16, 128), dB2 = make_desc(smem_u32(sB + 2 * NP * 4), NP * 16, 128);
-    const long long t0 = clock64();
-    for (int i = 0; i < iters; ++i) {
-      const uint32_t d = tb + (uint32_t)((i % n_acc) * NP);
-      umma_tf32(d, dA + (uint64_t)(i & 3), dB, idesc, i >= n_acc ? 1u : 0u);
-      if (split3) {
-        umma_tf32(d, dA2 + (uint64_t)(i & 3), dB, idesc, 1u);
-        umma_tf32(d, dA + (uint64_t)(i & 3), dB2, idesc, 1u);
+  if (threadIdx.x < 32) {
+    if (elect_one()) {
+      const uint64_t dA = make_desc(smem_u32(sA), a_pw * 16, 128), dA2 = make_desc(smem_u32(sA + 2 * 160 * 4), a_pw * 16, 128);
+      const uint64_t dB = make_desc(smem_u32(sB), NP * 16, 128), dB2 = make_desc(smem_u32(sB + 2 * NP * 4), NP * 16, 128);
+      const long long t0 = clock64();
+      for (int i = 0; i < iters; i += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t d = tb + (uint32_t)(((i + u) % n_acc) * NP);
+          umma_tf32(d, dA + (uint64_t)u, dB, idesc, (i + u) >= n_acc ? 1u : 0u);
+          if (split3) {
+            umma_tf32(d, dA2 + (uint64_t)u, dB, idesc, 1u);
+            umma_tf32(d, dA + (uint64_t)u, dB2, idesc, 1u);
+          }
+        }
       }
+      const long long t1 = clock64();
+      umma_commit(smem_u32(mbar));
+      mbar_wait(smem_u32(mbar), 0);
+      const long long t2 = clock64();
+      out[0] = t1 - t0; out[1] = t2 - t0;
     }
-    const long long t1 = clock64();
-    umma_commit(smem_u32(mbar));
-    mbar_wait(smem_u32(mbar), 0);
-    const long long t2 = clock64();
-    out[0] = t1 - t0; out[1] = t2 - t0;
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -515,13 +553,15 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(long long* out, int it
 }  // namespace risp
 
 // out: DEVICE long long[2] = {issue cycles, total cycles}.  Diagnostic entry (scripts/probe_mma_rate.py).
-extern "C" int risp_debug_mma_rate(long long* out, int NP, int iters, int n_acc, int split3, risp_stream_t stream) {
-  RISP_REQUIRE(out && (NP == 64 || NP == 128 || NP == 256) && iters > 0 && n_acc >= 1 && n_acc * NP <= 512, RISP_E_INVALID,
-               "risp_debug_mma_rate: bad arguments");
+// a_pw: pixels per k-group of the A operand (its LBO is a_pw*16 bytes), <= 160.
+extern "C" int risp_debug_mma_rate(long long* out, int NP, int iters, int n_acc, int split3, int a_pw, risp_stream_t stream) {
+  RISP_REQUIRE(out && (NP == 16 || NP == 32 || NP == 64 || NP == 128 || NP == 256) && iters > 0 && (iters % 4) == 0 && n_acc >= 1 &&
+                   n_acc * NP <= 512 && a_pw >= 128 && a_pw <= 160, RISP_E_INVALID, "risp_debug_mma_rate: bad arguments");
   const size_t smem = 64 * 1024;
   cudaStream_t st = as_stream(stream);
-  if (NP == 64) { cudaFuncSetAttribute(mma_rate_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); mma_rate_kernel<64><<<1, 128, smem, st>>>(out, iters, n_acc, split3); }
-  else if (NP == 128) { cudaFuncSetAttribute(mma_rate_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); mma_rate_kernel<128><<<1, 128, smem, st>>>(out, iters, n_acc, split3); }
-  else { cudaFuncSetAttribute(mma_rate_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); mma_rate_kernel<256><<<1, 128, smem, st>>>(out, iters, n_acc, split3); }
+#define RISP_RATE(NN) { cudaFuncSetAttribute(mma_rate_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+                        mma_rate_kernel<NN><<<1, 128, smem, st>>>(out, iters, n_acc, split3, a_pw); }
+  if (NP == 16) RISP_RATE(16) else if (NP == 32) RISP_RATE(32) else if (NP == 64) RISP_RATE(64) else if (NP == 128) RISP_RATE(128) else RISP_RATE(256)
+#undef RISP_RATE
   return check_launch("mma_rate_kernel");
 }
