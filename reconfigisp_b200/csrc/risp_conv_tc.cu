@@ -93,7 +93,14 @@ __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float (&v)[16]) {
 
 // ---- kernel ---------------------------------------------------------------------------------------------
 // K: filter size; CI_C: input channels per chunk (multiple of 8); R: output rows per CTA; NP: padded Cout (16/32/48/64);
-// TPS: filter taps per weight stage (divides K*K)
+// NBUF: weight-stage buffers (power of two); MINB: CTAs per SM the configuration is sized for
+//
+// Fat MMAs (measured on B200, scripts/probe_mma_rate.py): a 128 x N x 8 tf32 MMA with both operands in shared memory
+// costs max(N/2, (4 KB + N*32 B)/128 B per clk) + ~5 cycles, with a floor of ~46 -- N = 64 runs at 60 % of the tensor
+// rate, N = 16 at 17 %.  So the vertical taps are stacked ON N: for one staged input row i and one horizontal tap dx,
+// ONE MMA multiplies the row by [W(dy=K-1,dx) | ... | W(dy=0,dx)] (reversed so that consecutive column blocks belong
+// to consecutive output rows i-K+1 .. i) and lands directly in the TMEM accumulators of all the output rows that
+// input row feeds: N = min(rows fed, R) * NP <= 256, and the accumulators are laid out [row][NP] as the epilogue wants.
 //
 // Accuracy note (measured on B200): every tcgen05.mma rounds its fp32 accumulator once, toward zero, so the error
 // of one accumulator grows linearly with the number of MMAs chained into it (~6e-8 relative each).  The two
@@ -101,14 +108,14 @@ __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float (&v)[16]) {
 // accumulator then sees one rounding per 8 input channels per tap instead of three, and the roundings of the
 // small accumulator are 2^-11 times less significant.  The two accumulators are added in the epilogue.
 //
-// Pipeline of one CTA (two CTAs are resident per SM and fill each other's gaps):
-//   weights  : double-buffered stages of TPS taps, fetched by 1-D bulk async copies (TMA engine, no registers, no
-//              thread work) that signal bfull[buf] by complete_tx; the issuing lane refills a buffer as soon as the
-//              MMAs that read it have committed (mdone[buf])
+// Pipeline of one CTA:
+//   weights  : stages of one horizontal tap (all K vertical taps, one chunk), NBUF-deep ring filled by 1-D bulk async
+//              copies (TMA engine, no registers, no thread work) that signal bfull[buf] by complete_tx; the issuing
+//              lane refills a buffer as soon as the MMAs that read it have committed (mdone[buf])
 //   inputs   : the rows of the NEXT input-channel chunk are loaded into registers while the MMAs of the current
 //              chunk run, and only split (hi/lo) + stored once those MMAs have committed (afree, one phase per chunk)
-//   MMAs     : one elected lane of warp 0
-template <int K, int CI_C, int R, int NP, int TPS>
+//   MMAs     : one elected lane of warp 0; accumulators are zeroed with tcgen05.st up front so every MMA accumulates
+template <int K, int CI_C, int R, int NP, int NBUF, int MINB>
 struct TcCfg {
   static constexpr int PAD = K / 2;
   static constexpr int PW = TC_M + K - 1;                 // staged pixels per row
@@ -116,15 +123,17 @@ struct TcCfg {
   static constexpr int ROWS = R + K - 1;
   static constexpr int A_ROW_FLOATS = KG * PW * 4;        // one staged row, one precision
   static constexpr int A_FLOATS = ROWS * A_ROW_FLOATS;    // hi (lo follows)
-  static constexpr int B_TAP_FLOATS = KG * NP * 4;        // one tap, one precision
-  static constexpr int B_STAGE_FLOATS = TPS * B_TAP_FLOATS;
-  static constexpr int B_CHUNK_FLOATS = K * K * B_TAP_FLOATS;
-  static constexpr int NST = K * K / TPS;                 // weight stages per chunk
-  static_assert((K * K) % TPS == 0, "taps per stage must divide K*K");
-  static constexpr size_t SMEM = sizeof(float) * (2 * A_FLOATS + 4 * B_STAGE_FLOATS) + 64;
+  static constexpr int NSTACK = K * NP;                   // GEMM-N rows of one weight stage: [dy reversed][co]
+  static constexpr int B_STAGE_FLOATS = KG * NSTACK * 4;  // one horizontal tap, one precision
+  static constexpr int B_CHUNK_FLOATS = K * B_STAGE_FLOATS;
+  static constexpr int NST = K;                           // weight stages per chunk
+  static constexpr size_t SMEM = sizeof(float) * (2 * A_FLOATS + 2 * NBUF * B_STAGE_FLOATS) + 128;
   static constexpr int ACC_COLS = 2 * R * NP;             // main + cross-term accumulators
   static constexpr int TMEM_COLS = (ACC_COLS <= 32) ? 32 : (ACC_COLS <= 64) ? 64 : (ACC_COLS <= 128) ? 128 : (ACC_COLS <= 256) ? 256 : 512;
   static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
+  static_assert(TMEM_COLS * MINB <= 512, "TMEM oversubscribed");
+  static_assert((R < K ? R : K) * NP <= 256, "MMA N exceeds 256");
+  static_assert((NBUF & (NBUF - 1)) == 0 && NBUF >= 2, "NBUF must be a power of two");
   static constexpr int A_TOTAL = ROWS * KG * PW;          // float4 elements staged per chunk
   static constexpr int A_ITER = (A_TOTAL + TC_THREADS - 1) / TC_THREADS;
 };
@@ -136,18 +145,23 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
+// zero 16 consecutive TMEM columns of this warp's 32 lanes
+__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
+               ::"r"(taddr), "r"(0u) : "memory");
+}
 
-template <int K, int CI_C, int R, int NP, int TPS>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+template <int K, int CI_C, int R, int NP, int NBUF, int MINB>
+__global__ void __launch_bounds__(TC_THREADS, MINB)
 conv_tc_kernel(ConvTcArgs a) {
-  using C = TcCfg<K, CI_C, R, NP, TPS>;
+  using C = TcCfg<K, CI_C, R, NP, NBUF, MINB>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* sA_hi = reinterpret_cast<float*>(smem_raw);
   float* sA_lo = sA_hi + C::A_FLOATS;
   float* sB = sA_lo + C::A_FLOATS;                         // [buf][hi|lo][B_STAGE_FLOATS]
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(sB + 4 * C::B_STAGE_FLOATS);   // bfull[2], mdone[2], afree
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 5);
-  const uint32_t bfull = smem_u32(mbar), mdone = smem_u32(mbar + 2), afree = smem_u32(mbar + 4);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sB + 2 * NBUF * C::B_STAGE_FLOATS);   // bfull[NBUF], mdone[NBUF], afree
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2 * NBUF + 1);
+  const uint32_t bfull = smem_u32(mbar), mdone = smem_u32(mbar + NBUF), afree = smem_u32(mbar + 2 * NBUF);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int strips = (a.W + TC_M - 1) / TC_M;
@@ -162,15 +176,13 @@ conv_tc_kernel(ConvTcArgs a) {
   }
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < 5; ++i) mbar_init(smem_u32(mbar + i), 1);
+    for (int i = 0; i < 2 * NBUF + 1; ++i) mbar_init(smem_u32(mbar + i), 1);
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // instruction descriptor: D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2, K-major both, N>>3 [17,23), M>>4 [24,29)
-  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
   const int n_chunks = (a.CinG * 4 + CI_C - 1) / CI_C;
   const int n_stages = n_chunks * C::NST;
@@ -180,18 +192,18 @@ conv_tc_kernel(ConvTcArgs a) {
   const long long lo_off = (long long)n_chunks * C::B_CHUNK_FLOATS;
   constexpr uint32_t kStageBytes = C::B_STAGE_FLOATS * 4;
 
-  // weight stage s -> buffer s&1 (hi block then lo block); issued by the MMA lane only
+  // weight stage s -> buffer s % NBUF (hi block then lo block); issued by the MMA lane only
   auto fetch_weights = [&](int s) {
-    const int c = s / C::NST, st = s % C::NST;
-    const long long off = (long long)c * C::B_CHUNK_FLOATS + (long long)st * C::B_STAGE_FLOATS;
-    const uint32_t bar = bfull + 8u * (uint32_t)(s & 1);
-    const uint32_t dst = smem_u32(sB) + (uint32_t)(s & 1) * 2u * kStageBytes;
+    const long long off = (long long)s * C::B_STAGE_FLOATS;              // stages are contiguous: [chunk][dx]
+    const uint32_t b = (uint32_t)(s & (NBUF - 1));
+    const uint32_t bar = bfull + 8u * b;
+    const uint32_t dst = smem_u32(sB) + b * 2u * kStageBytes;
     mbar_expect_tx(bar, 2u * kStageBytes);
     bulk_g2s(dst, a.wprep + off, kStageBytes, bar);
     bulk_g2s(dst + kStageBytes, a.wprep + lo_off + off, kStageBytes, bar);
   };
 
-  // input rows of chunk c -> registers (zero padding, optional mask / ReLU applied here so only one array stays live)
+  // input rows of chunk c -> registers (zero padding, optional mask applied here so only one array stays live)
   float4 v[C::A_ITER];
   auto load_inputs = [&](int c) {
 #pragma unroll
@@ -231,20 +243,30 @@ conv_tc_kernel(ConvTcArgs a) {
     }
   };
 
-  // ---- prologue: weights of stage 0 in flight, inputs of chunk 0 staged ----
+  // ---- prologue: first weight stages in flight, accumulators zeroed, inputs of chunk 0 staged ----
   if (warp == 0) {
-    if (elect_one()) fetch_weights(0);
+    if (elect_one()) {
+      for (int s = 0; s < NBUF - 1 && s < n_stages; ++s) fetch_weights(s);
+    }
     __syncwarp();
   }
   load_inputs(0);
+  {
+    // warp w owns TMEM lanes 32*(w%4)..; the two warp sets split the 16-column groups
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll
+    for (int g = 0; g < C::ACC_COLS / 16; ++g)
+      if ((g & 1) == (warp >> 2)) tmem_zero16(lane_base + (uint32_t)(g * 16));
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
   store_inputs();
   fence_async_smem();        // generic-proxy smem writes -> visible to the tensor-core (async) proxy
   tc_fence_before();
   __syncthreads();
 
   for (int s = 0; s < n_stages; ++s) {
-    const int c = s / C::NST, st = s % C::NST;
-    if (st == 0 && s > 0) {
+    const int c = s / C::NST, dx = s % C::NST;
+    if (dx == 0 && s > 0) {
       // chunk boundary: the MMAs of chunk c-1 (the only readers of the input tile) must have committed
       mbar_wait(afree, (uint32_t)((c - 1) & 1));
       store_inputs();          // registers were loaded while those MMAs ran
@@ -254,43 +276,46 @@ conv_tc_kernel(ConvTcArgs a) {
     }
     if (warp == 0) {
       if (elect_one()) {
-        mbar_wait(bfull + 8u * (uint32_t)(s & 1), (uint32_t)((s >> 1) & 1));
+        const uint32_t b = (uint32_t)(s & (NBUF - 1));
+        mbar_wait(bfull + 8u * b, (uint32_t)((s / NBUF) & 1));
         tc_fence_after();
-        const uint32_t sBh = smem_u32(sB) + (uint32_t)(s & 1) * 2u * kStageBytes, sBl = sBh + kStageBytes;
-#pragma unroll 1
-        for (int tl = 0; tl < TPS; ++tl) {
-          const int tap = st * TPS + tl;
-          const int dy = tap / K, dx = tap % K;
+        const uint32_t sBh = smem_u32(sB) + b * 2u * kStageBytes, sBl = sBh + kStageBytes;
+        const uint32_t a_dx = (uint32_t)(dx * 16);
 #pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const uint32_t d_main = tmem_base + (uint32_t)(r * NP);
-            const uint32_t d_cross = tmem_base + (uint32_t)((R + r) * NP);
+        for (int i = 0; i < C::ROWS; ++i) {
+          // input row i feeds output rows r_lo..r_hi; their weights are the column blocks j0.. of the stage
+          constexpr int dummy = 0; (void)dummy;
+          const int r_lo = (i - K + 1 > 0) ? i - K + 1 : 0;
+          const int r_hi = (i < R - 1) ? i : R - 1;
+          const int nrows = r_hi - r_lo + 1;
+          const int j0 = r_lo - (i - K + 1);
+          const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((nrows * NP) >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+          const uint32_t d_main = tmem_base + (uint32_t)(r_lo * NP);
+          const uint32_t d_cross = tmem_base + (uint32_t)((R + r_lo) * NP);
 #pragma unroll
-            for (int ks = 0; ks < C::KG / 2; ++ks) {
-              const uint32_t a_off = (uint32_t)((r + dy) * C::A_ROW_FLOATS * 4 + (2 * ks) * C::PW * 16 + dx * 16);
-              const uint32_t b_off = (uint32_t)((tl * C::KG + 2 * ks) * NP * 16);
-              const uint64_t dAh = make_desc(smem_u32(sA_hi) + a_off, C::PW * 16, 128);
-              const uint64_t dAl = make_desc(smem_u32(sA_lo) + a_off, C::PW * 16, 128);
-              const uint64_t dBh = make_desc(sBh + b_off, NP * 16, 128);
-              const uint64_t dBl = make_desc(sBl + b_off, NP * 16, 128);
-              const uint32_t acc = (s == 0 && tl == 0 && ks == 0) ? 0u : 1u;
-              umma_tf32(d_main, dAh, dBh, idesc, acc);
-              umma_tf32(d_cross, dAl, dBh, idesc, acc);
-              umma_tf32(d_cross, dAh, dBl, idesc, 1u);
-            }
+          for (int ks = 0; ks < C::KG / 2; ++ks) {
+            const uint32_t a_off = (uint32_t)(i * C::A_ROW_FLOATS * 4 + (2 * ks) * C::PW * 16) + a_dx;
+            const uint32_t b_off = (uint32_t)((2 * ks) * C::NSTACK * 16 + j0 * NP * 16);
+            const uint64_t dAh = make_desc(smem_u32(sA_hi) + a_off, C::PW * 16, 128);
+            const uint64_t dAl = make_desc(smem_u32(sA_lo) + a_off, C::PW * 16, 128);
+            const uint64_t dBh = make_desc(sBh + b_off, C::NSTACK * 16, 128);
+            const uint64_t dBl = make_desc(sBl + b_off, C::NSTACK * 16, 128);
+            umma_tf32(d_main, dAh, dBh, idesc, 1u);
+            umma_tf32(d_cross, dAl, dBh, idesc, 1u);
+            umma_tf32(d_cross, dAh, dBl, idesc, 1u);
           }
         }
-        umma_commit(mdone + 8u * (uint32_t)(s & 1));
-        if (st == C::NST - 1) umma_commit(afree);            // one phase per chunk (and the last one gates the epilogue)
-        if (s + 1 < n_stages) {
-          // the other weight buffer was last read by stage s-1
-          if (s >= 1) mbar_wait(mdone + 8u * (uint32_t)((s + 1) & 1), (uint32_t)(((s - 1) >> 1) & 1));
-          fetch_weights(s + 1);
+        umma_commit(mdone + 8u * b);
+        if (dx == C::NST - 1) umma_commit(afree);            // one phase per chunk (and the last one gates the epilogue)
+        const int sn = s + NBUF - 1;                          // refill the buffer stage s-1 used
+        if (sn < n_stages) {
+          if (s >= 1) mbar_wait(mdone + 8u * (uint32_t)(sn & (NBUF - 1)), (uint32_t)(((s - 1) / NBUF) & 1));
+          fetch_weights(sn);
         }
       }
       __syncwarp();
     }
-    if (st == C::NST - 1 && c + 1 < n_chunks) load_inputs(c + 1);   // in flight while this chunk's MMAs run
+    if (dx == C::NST - 1 && c + 1 < n_chunks) load_inputs(c + 1);   // in flight while this chunk's MMAs run
   }
   // ---- epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).., and the (w/4)-th half of the 16-column groups ----
   mbar_wait(afree, (uint32_t)((n_chunks - 1) & 1));
@@ -355,20 +380,22 @@ conv_tc_kernel(ConvTcArgs a) {
   }
 }
 
-// weights (Cout,Cin,K,K) -> [chunk][dy][dx][kg][NP][4] hi block, then lo block.  transpose_flip: data-gradient operator.
+// weights (Cout,Cin,K,K) -> [chunk][dx][kg][j = K-1-dy][NP][4] hi block, then the lo block.
+// transpose_flip: data-gradient operator.
 __global__ void conv_tc_prepare_kernel(const float* __restrict__ w, float* __restrict__ out, int Cin, int Cout, int K, int CI_C,
                                        int NP, int transpose_flip, long long total) {
   const int rows = transpose_flip ? Cout : Cin, cols = transpose_flip ? Cin : Cout;   // rows = GEMM-K channels, cols = GEMM-N
   const int KG = CI_C / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long t = i;
-    const int j = (int)(t % 4); t /= 4;
+    const int e = (int)(t % 4); t /= 4;
     const int co = (int)(t % NP); t /= NP;
+    const int jr = (int)(t % K); t /= K;
     const int kg = (int)(t % KG); t /= KG;
     const int dx = (int)(t % K); t /= K;
-    const int dy = (int)(t % K); t /= K;
     const int chunk = (int)t;
-    const int ci = chunk * CI_C + kg * 4 + j;
+    const int dy = K - 1 - jr;
+    const int ci = chunk * CI_C + kg * 4 + e;
     float v = 0.f;
     if (ci < rows && co < cols) {
       if (!transpose_flip) v = w[(((long long)co * Cin + ci) * K + dy) * K + dx];
@@ -413,19 +440,20 @@ __global__ void from_blocked_kernel(const float* __restrict__ src, float* __rest
   }
 }
 
-template <int K, int CI_C, int R, int NP, int TPS>
+template <int K, int CI_C, int R, int NP, int NBUF, int MINB>
 static int launch_tc(const ConvTcArgs& a, int N, cudaStream_t st) {
-  using C = TcCfg<K, CI_C, R, NP, TPS>;
+  using C = TcCfg<K, CI_C, R, NP, NBUF, MINB>;
+  static_assert(C::SMEM <= 227 * 1024 / MINB - 1024 * (MINB > 1), "shared memory budget");
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(conv_tc_kernel<K, CI_C, R, NP, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_tc_kernel<K, CI_C, R, NP, NBUF, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess) {
       set_error("conv_tc: cannot opt in to %zu bytes of shared memory", C::SMEM);
       return RISP_E_CUDA;
     }
     attr = true;
   }
   dim3 grid((unsigned)(cdiv(a.W, TC_M) * cdiv(a.H, R)), (unsigned)N);
-  conv_tc_kernel<K, CI_C, R, NP, TPS><<<grid, TC_THREADS, C::SMEM, st>>>(a);
+  conv_tc_kernel<K, CI_C, R, NP, NBUF, MINB><<<grid, TC_THREADS, C::SMEM, st>>>(a);
   return check_launch("conv_tc_kernel");
 }
 
@@ -484,18 +512,18 @@ extern "C" int risp_conv_tc_fwd(const float* x_blk, const float* mask_in_blk, co
   const int NP = (Cout + 15) / 16 * 16;
   ConvTcArgs a{x_blk, wprep, bias, res_blk, mask_in_blk, mask_out_blk, y_blk, y_planar, risp_conv_tc_padded_channels(Cin) / 4, Cout, NP, H, W, flags};
   cudaStream_t st = as_stream(stream);
-#define RISP_TC(KK, RR, NN, TT) return launch_tc<KK, 8, RR, NN, TT>(a, N, st)
-  // rows per CTA: 2*R*NP TMEM columns <= 256 and shared memory <= ~112 KB so that two CTAs are resident per SM;
-  // TT = filter taps per (double-buffered) weight stage
+#define RISP_TC(KK, RR, NN, BB, MM) return launch_tc<KK, 8, RR, NN, BB, MM>(a, N, st)
+  // R rows per CTA: the fattest MMA has N = min(R,K)*NP <= 256; TMEM columns = 2*R*NP per CTA.  MM = 2 CTAs per SM
+  // where 2*R*NP <= 256 and shared memory <= ~112 KB, otherwise one CTA with twice the rows.  BB = weight-stage ring depth.
   switch (K) {
     case 1:
-      switch (NP) { case 16: RISP_TC(1, 8, 16, 1); case 32: RISP_TC(1, 4, 32, 1); case 48: RISP_TC(1, 2, 48, 1); default: RISP_TC(1, 2, 64, 1); }
+      switch (NP) { case 16: RISP_TC(1, 8, 16, 4, 2); case 32: RISP_TC(1, 4, 32, 4, 2); case 48: RISP_TC(1, 2, 48, 4, 2); default: RISP_TC(1, 2, 64, 4, 2); }
     case 3:
-      switch (NP) { case 16: RISP_TC(3, 8, 16, 9); case 32: RISP_TC(3, 4, 32, 9); case 48: RISP_TC(3, 2, 48, 9); default: RISP_TC(3, 2, 64, 9); }
+      switch (NP) { case 16: RISP_TC(3, 8, 16, 4, 2); case 32: RISP_TC(3, 4, 32, 4, 2); case 48: RISP_TC(3, 2, 48, 4, 2); default: RISP_TC(3, 2, 64, 4, 2); }
     case 5:
-      switch (NP) { case 16: RISP_TC(5, 4, 16, 5); case 32: RISP_TC(5, 4, 32, 5); case 48: RISP_TC(5, 2, 48, 5); default: RISP_TC(5, 2, 64, 5); }
+      switch (NP) { case 16: RISP_TC(5, 4, 16, 4, 2); case 32: RISP_TC(5, 4, 32, 4, 2); case 48: RISP_TC(5, 2, 48, 2, 2); default: RISP_TC(5, 2, 64, 2, 2); }
     default:
-      switch (NP) { case 16: RISP_TC(9, 2, 16, 9); case 32: RISP_TC(9, 2, 32, 3); case 48: RISP_TC(9, 2, 48, 3); default: RISP_TC(9, 2, 64, 3); }
+      switch (NP) { case 16: RISP_TC(9, 8, 16, 4, 1); case 32: RISP_TC(9, 4, 32, 2, 1); case 48: RISP_TC(9, 4, 48, 2, 1); default: RISP_TC(9, 4, 64, 2, 1); }
   }
 #undef RISP_TC
 }
