@@ -289,6 +289,9 @@ int risp_conv_tc_fwd(const float* x_blk, const float* mask_in_blk, const float* 
 
 /* Diagnostic: cycles to issue / complete `iters` tcgen05 tf32 MMAs (M=128, N=NP, K=8) from one thread with the
  * operand layout of risp_conv_tc_fwd.  out: DEVICE long long[2] = {issue cycles, total cycles}. */
+/* Diagnostic: per-phase clock64 timeline of one CTA of the last tensor-core convolution (builds with -DRISP_TC_TRACE only;
+ * zeros otherwise).  out_host: HOST long long[16]. */
+int risp_debug_tc_trace(long long* out_host);
 int risp_debug_mma_rate(long long* out, int NP, int iters, int n_acc, int split3, int a_pw, risp_stream_t stream);
 
 #ifdef __cplusplus

@@ -88,8 +88,8 @@ __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float (&v)[16]) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- kernel ---------------------------------------------------------------------------------------------
 // K: filter size; CI_C: input channels per chunk (multiple of 8); R: output rows per CTA; NP: padded Cout (16/32/48/64);
@@ -127,7 +127,7 @@ struct TcCfg {
   static constexpr int B_STAGE_FLOATS = KG * NSTACK * 4;  // one horizontal tap, one precision
   static constexpr int B_CHUNK_FLOATS = K * B_STAGE_FLOATS;
   static constexpr int NST = K;                           // weight stages per chunk
-  static constexpr size_t SMEM = sizeof(float) * (2 * A_FLOATS + 2 * NBUF * B_STAGE_FLOATS) + 128;
+  static constexpr size_t SMEM = sizeof(float) * (2 * A_FLOATS + 2 * NBUF * B_STAGE_FLOATS) + 128 + 256;   // + barriers + bias
   static constexpr int ACC_COLS = 2 * R * NP;             // main + cross-term accumulators
   static constexpr int TMEM_COLS = (ACC_COLS <= 32) ? 32 : (ACC_COLS <= 64) ? 64 : (ACC_COLS <= 128) ? 128 : (ACC_COLS <= 256) ? 256 : 512;
   static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
@@ -135,7 +135,8 @@ struct TcCfg {
   static_assert((R < K ? R : K) * NP <= 256, "MMA N exceeds 256");
   static_assert((NBUF & (NBUF - 1)) == 0 && NBUF >= 2, "NBUF must be a power of two");
   static constexpr int A_TOTAL = ROWS * KG * PW;          // float4 elements staged per chunk
-  static constexpr int A_ITER = (A_TOTAL + TC_THREADS - 1) / TC_THREADS;
+  static constexpr int STAGERS = TC_THREADS - 32;         // warp 0 only issues MMAs / weight fetches; warps 1..7 stage inputs
+  static constexpr int A_ITER = (A_TOTAL + STAGERS - 1) / STAGERS;
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
@@ -151,6 +152,16 @@ __device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
                ::"r"(taddr), "r"(0u) : "memory");
 }
 
+// optional in-kernel timeline of one CTA (build with -DRISP_TC_TRACE; read back with risp_debug_tc_trace)
+__device__ long long g_tc_trace[16];
+#ifdef RISP_TC_TRACE
+#define TC_TRACE(slot) do { if (trace_cta && tid == 0) g_tc_trace[slot] = clock64(); } while (0)
+#define TC_TRACE_ADD(slot, t_begin) do { if (trace_cta) g_tc_trace[slot] += clock64() - (t_begin); } while (0)
+#else
+#define TC_TRACE(slot) do { } while (0)
+#define TC_TRACE_ADD(slot, t_begin) do { } while (0)
+#endif
+
 template <int K, int CI_C, int R, int NP, int NBUF, int MINB>
 __global__ void __launch_bounds__(TC_THREADS, MINB)
 conv_tc_kernel(ConvTcArgs a) {
@@ -161,6 +172,7 @@ conv_tc_kernel(ConvTcArgs a) {
   float* sB = sA_lo + C::A_FLOATS;                         // [buf][hi|lo][B_STAGE_FLOATS]
   uint64_t* mbar = reinterpret_cast<uint64_t*>(sB + 2 * NBUF * C::B_STAGE_FLOATS);   // bfull[NBUF], mdone[NBUF], afree
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2 * NBUF + 1);
+  float* s_bias = reinterpret_cast<float*>(mbar + 16);     // 64 floats, zero beyond Cout / without a bias
   const uint32_t bfull = smem_u32(mbar), mdone = smem_u32(mbar + NBUF), afree = smem_u32(mbar + 2 * NBUF);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -169,6 +181,12 @@ conv_tc_kernel(ConvTcArgs a) {
   const int y0 = (blockIdx.x / strips) * R;
   const int n = blockIdx.y;
   const bool relu_in = (a.flags & RISP_CONV_RELU_IN) != 0;
+#ifdef RISP_TC_TRACE
+  const bool trace_cta = blockIdx.x == 5 && blockIdx.y == 0;
+  if (trace_cta && tid == 0) { for (int i = 0; i < 16; ++i) g_tc_trace[i] = 0; }
+  long long tq = 0; (void)tq;
+#endif
+  TC_TRACE(0);
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::TMEM_COLS) : "memory");
@@ -178,6 +196,7 @@ conv_tc_kernel(ConvTcArgs a) {
 #pragma unroll
     for (int i = 0; i < 2 * NBUF + 1; ++i) mbar_init(smem_u32(mbar + i), 1);
   }
+  if (tid >= 64 && tid < 128) s_bias[tid - 64] = (a.bias && tid - 64 < a.Cout) ? __ldg(a.bias + tid - 64) : 0.f;
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   tc_fence_before();
   __syncthreads();
@@ -203,32 +222,57 @@ conv_tc_kernel(ConvTcArgs a) {
     bulk_g2s(dst + kStageBytes, a.wprep + lo_off + off, kStageBytes, bar);
   };
 
-  // input rows of chunk c -> registers (zero padding, optional mask applied here so only one array stays live)
+  // input rows of chunk c -> registers (zero padding; the optional mask is applied here so only one array stays live).
+  // The unmasked path must not contain any use of the loaded values: a (predicated-off) select right behind a load
+  // still waits for it and would serialise the L2 latency of every element.
   float4 v[C::A_ITER];
+  auto input_offset = [&](int it, int c, long long& o) -> bool {
+    const int i = (tid - 32) + it * C::STAGERS;
+    const int px = i % C::PW;
+    const int kg = (i / C::PW) % C::KG;
+    const int row = i / (C::PW * C::KG);
+    const int gy = y0 - C::PAD + row, gx = x0 - C::PAD + px, gkg = c * C::KG + kg;
+    o = (long long)gy * row_stride + ((long long)gkg * a.W + gx) * 4;
+    return i < C::A_TOTAL && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && gkg < a.CinG;
+  };
   auto load_inputs = [&](int c) {
+    if (warp == 0) return;
+    if (!min_) {
 #pragma unroll
-    for (int it = 0; it < C::A_ITER; ++it) {
-      const int i = tid + it * TC_THREADS;
-      const int px = i % C::PW;
-      const int kg = (i / C::PW) % C::KG;
-      const int row = i / (C::PW * C::KG);
-      const int gy = y0 - C::PAD + row, gx = x0 - C::PAD + px, gkg = c * C::KG + kg;
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i < C::A_TOTAL && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && gkg < a.CinG) {
-        const long long o = (long long)gy * row_stride + ((long long)gkg * a.W + gx) * 4;
-        t = __ldg(reinterpret_cast<const float4*>(xin + o));
-        if (min_) {
-          const float4 m = __ldg(reinterpret_cast<const float4*>(min_ + o));
-          t.x = m.x > 0.f ? t.x : 0.f; t.y = m.y > 0.f ? t.y : 0.f; t.z = m.z > 0.f ? t.z : 0.f; t.w = m.w > 0.f ? t.w : 0.f;
+      for (int it = 0; it < C::A_ITER; ++it) {
+        long long o;
+        const bool ok = input_offset(it, c, o);
+        v[it] = ok ? __ldg(reinterpret_cast<const float4*>(xin + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else {
+      // masked (data-gradient) path: groups of four elements, eight loads in flight per group
+#pragma unroll
+      for (int g = 0; g < C::A_ITER; g += 4) {
+        float4 m[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (g + u < C::A_ITER) {
+            long long o;
+            const bool ok = input_offset(g + u, c, o);
+            v[g + u] = ok ? __ldg(reinterpret_cast<const float4*>(xin + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            m[u] = ok ? __ldg(reinterpret_cast<const float4*>(min_ + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (g + u < C::A_ITER) {
+            float4& t = v[g + u];
+            t.x = m[u].x > 0.f ? t.x : 0.f; t.y = m[u].y > 0.f ? t.y : 0.f; t.z = m[u].z > 0.f ? t.z : 0.f; t.w = m[u].w > 0.f ? t.w : 0.f;
+          }
         }
       }
-      v[it] = t;
     }
   };
   auto store_inputs = [&]() {
+    if (warp == 0) return;
 #pragma unroll
     for (int it = 0; it < C::A_ITER; ++it) {
-      const int i = tid + it * TC_THREADS;
+      const int i = (tid - 32) + it * C::STAGERS;
       float4 t = v[it];
       if (relu_in) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
       float4 hi, lo;
@@ -250,7 +294,9 @@ conv_tc_kernel(ConvTcArgs a) {
     }
     __syncwarp();
   }
+  TC_TRACE(5);
   load_inputs(0);
+  TC_TRACE(6);
   {
     // warp w owns TMEM lanes 32*(w%4)..; the two warp sets split the 16-column groups
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
@@ -259,25 +305,47 @@ conv_tc_kernel(ConvTcArgs a) {
       if ((g & 1) == (warp >> 2)) tmem_zero16(lane_base + (uint32_t)(g * 16));
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
+  TC_TRACE(7);
   store_inputs();
+  TC_TRACE(14);
   fence_async_smem();        // generic-proxy smem writes -> visible to the tensor-core (async) proxy
   tc_fence_before();
   __syncthreads();
+  TC_TRACE(1);
 
   for (int s = 0; s < n_stages; ++s) {
     const int c = s / C::NST, dx = s % C::NST;
     if (dx == 0 && s > 0) {
       // chunk boundary: the MMAs of chunk c-1 (the only readers of the input tile) must have committed
+#ifdef RISP_TC_TRACE
+      tq = clock64();
+#endif
       mbar_wait(afree, (uint32_t)((c - 1) & 1));
+      if (tid == 0) TC_TRACE_ADD(8, tq);
+#ifdef RISP_TC_TRACE
+      tq = clock64();
+#endif
       store_inputs();          // registers were loaded while those MMAs ran
+      if (tid == 0) TC_TRACE_ADD(12, tq);
+#ifdef RISP_TC_TRACE
+      tq = clock64();
+#endif
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
+      if (tid == 0) TC_TRACE_ADD(13, tq);
     }
     if (warp == 0) {
       if (elect_one()) {
         const uint32_t b = (uint32_t)(s & (NBUF - 1));
+#ifdef RISP_TC_TRACE
+        tq = clock64();
+#endif
         mbar_wait(bfull + 8u * b, (uint32_t)((s / NBUF) & 1));
+        TC_TRACE_ADD(9, tq);
+#ifdef RISP_TC_TRACE
+        tq = clock64();
+#endif
         tc_fence_after();
         const uint32_t sBh = smem_u32(sB) + b * 2u * kStageBytes, sBl = sBh + kStageBytes;
         const uint32_t a_dx = (uint32_t)(dx * 16);
@@ -307,19 +375,26 @@ conv_tc_kernel(ConvTcArgs a) {
         }
         umma_commit(mdone + 8u * b);
         if (dx == C::NST - 1) umma_commit(afree);            // one phase per chunk (and the last one gates the epilogue)
+        TC_TRACE_ADD(10, tq);
+#ifdef RISP_TC_TRACE
+        tq = clock64();
+#endif
         const int sn = s + NBUF - 1;                          // refill the buffer stage s-1 used
         if (sn < n_stages) {
           if (s >= 1) mbar_wait(mdone + 8u * (uint32_t)(sn & (NBUF - 1)), (uint32_t)(((s - 1) / NBUF) & 1));
           fetch_weights(sn);
         }
+        TC_TRACE_ADD(11, tq);
       }
       __syncwarp();
     }
-    if (dx == C::NST - 1 && c + 1 < n_chunks) load_inputs(c + 1);   // in flight while this chunk's MMAs run
+    if (dx == 0 && c + 1 < n_chunks) load_inputs(c + 1);   // next chunk's rows: in flight while this chunk's MMAs run
   }
   // ---- epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).., and the (w/4)-th half of the 16-column groups ----
+  TC_TRACE(2);
   mbar_wait(afree, (uint32_t)((n_chunks - 1) & 1));
   tc_fence_after();
+  TC_TRACE(3);
   const bool relu_out = (a.flags & RISP_CONV_RELU_OUT) != 0, add_res = (a.flags & RISP_CONV_ADD_RES) != 0,
              res_relu = (a.flags & RISP_CONV_RES_RELU) != 0;
   const int lq = warp & 3, half = warp >> 2;
@@ -336,6 +411,7 @@ conv_tc_kernel(ConvTcArgs a) {
       float v[16], vc[16];
       tmem_ld<16>(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(r * NP + cb * 16), v);
       tmem_ld<16>(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)((R + r) * NP + cb * 16), vc);
+      tmem_ld_wait();
 #pragma unroll
       for (int q = 0; q < 16; ++q) v[q] += vc[q];
       if (gy < a.H && gx < a.W) {
@@ -343,11 +419,9 @@ conv_tc_kernel(ConvTcArgs a) {
         for (int q = 0; q < 4; ++q) {
           const int co = cb * 16 + q * 4;
           float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-          if (a.bias) {
-            if (co < a.Cout) o.x += __ldg(a.bias + co);
-            if (co + 1 < a.Cout) o.y += __ldg(a.bias + co + 1);
-            if (co + 2 < a.Cout) o.z += __ldg(a.bias + co + 2);
-            if (co + 3 < a.Cout) o.w += __ldg(a.bias + co + 3);
+          {
+            const float4 bb = *reinterpret_cast<const float4*>(s_bias + co);
+            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
           }
           if (relu_out) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
           const long long ob = ((long long)n * a.H + gy) * orow + ((long long)(co / 4) * a.W + gx) * 4;
@@ -375,6 +449,7 @@ conv_tc_kernel(ConvTcArgs a) {
   }
   tc_fence_before();
   __syncthreads();
+  TC_TRACE(4);
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
   }
@@ -526,6 +601,16 @@ extern "C" int risp_conv_tc_fwd(const float* x_blk, const float* mask_in_blk, co
       switch (NP) { case 16: RISP_TC(9, 8, 16, 4, 1); case 32: RISP_TC(9, 4, 32, 2, 1); case 48: RISP_TC(9, 4, 48, 2, 1); default: RISP_TC(9, 4, 64, 2, 1); }
   }
 #undef RISP_TC
+}
+
+// Timeline of the traced CTA of the last conv_tc launch (only meaningful in a -DRISP_TC_TRACE build): out = HOST
+// long long[16]: [0..4] clock64 at start / prologue done / all stages issued / MMAs done / end, [8] cycles waiting at
+// chunk boundaries, [9] waiting for weights, [10] issuing MMAs, [11] waiting to refill + issuing the weight fetch.
+extern "C" int risp_debug_tc_trace(long long* out_host) {
+  RISP_REQUIRE(out_host, RISP_E_INVALID, "risp_debug_tc_trace: null output");
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out_host, risp::g_tc_trace, sizeof(long long) * 16) != cudaSuccess) { set_error("risp_debug_tc_trace: copy failed"); return RISP_E_CUDA; }
+  return RISP_OK;
 }
 
 // ---- micro-benchmark: raw tcgen05 tf32 issue / execution rate for the operand layout used above ---------------
