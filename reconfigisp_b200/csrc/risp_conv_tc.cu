@@ -93,7 +93,8 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // ---- kernel ---------------------------------------------------------------------------------------------
 // K: filter size; CI_C: input channels per chunk (multiple of 8); R: output rows per CTA; NP: padded Cout (16/32/48/64);
-// NBUF: weight-stage buffers (power of two); MINB: CTAs per SM the configuration is sized for
+// NBUF: weight-stage buffers; MINB: CTAs per SM the configuration is sized for; ABUF: input-tile buffers (1 or 2);
+// PF: input chunks prefetched in registers (1 or 2); DXS: horizontal taps per weight stage (divides K)
 //
 // Fat MMAs (measured on B200, scripts/probe_mma_rate.py): a 128 x N x 8 tf32 MMA with both operands in shared memory
 // costs max(N/2, (4 KB + N*32 B)/128 B per clk) + ~5 cycles, with a floor of ~46 -- N = 64 runs at 60 % of the tensor
@@ -113,9 +114,12 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //              copies (TMA engine, no registers, no thread work) that signal bfull[buf] by complete_tx; the issuing
 //              lane refills a buffer as soon as the MMAs that read it have committed (mdone[buf])
 //   inputs   : the rows of the NEXT input-channel chunk are loaded into registers while the MMAs of the current
-//              chunk run, and only split (hi/lo) + stored once those MMAs have committed (afree, one phase per chunk)
+//              chunk run, then split (hi/lo) + stored once the MMAs that read the target buffer have committed
+//              (afree[buf]).  With ABUF = 2 that is the chunk before the current one, so the MMA stream never drains
+//              at a chunk boundary; with ABUF = 1 the second resident CTA fills the gap.  With PF = 2 a second
+//              register set keeps the loads TWO chunks ahead: a small-K chunk's MMAs are shorter than one L2 round trip
 //   MMAs     : one elected lane of warp 0; accumulators are zeroed with tcgen05.st up front so every MMA accumulates
-template <int K, int CI_C, int R, int NP, int NBUF, int MINB>
+template <int K, int CI_C, int R, int NP, int NBUF, int MINB, int ABUF, int PF, int DXS>
 struct TcCfg {
   static constexpr int PAD = K / 2;
   static constexpr int PW = TC_M + K - 1;                 // staged pixels per row
@@ -124,16 +128,18 @@ struct TcCfg {
   static constexpr int A_ROW_FLOATS = KG * PW * 4;        // one staged row, one precision
   static constexpr int A_FLOATS = ROWS * A_ROW_FLOATS;    // hi (lo follows)
   static constexpr int NSTACK = K * NP;                   // GEMM-N rows of one weight stage: [dy reversed][co]
-  static constexpr int B_STAGE_FLOATS = KG * NSTACK * 4;  // one horizontal tap, one precision
-  static constexpr int B_CHUNK_FLOATS = K * B_STAGE_FLOATS;
-  static constexpr int NST = K;                           // weight stages per chunk
-  static constexpr size_t SMEM = sizeof(float) * (2 * A_FLOATS + 2 * NBUF * B_STAGE_FLOATS) + 128 + 256;   // + barriers + bias
+  static constexpr int B_TAP_FLOATS = KG * NSTACK * 4;    // one horizontal tap, one precision
+  static constexpr int B_STAGE_FLOATS = DXS * B_TAP_FLOATS;
+  static constexpr int B_CHUNK_FLOATS = K * B_TAP_FLOATS;
+  static constexpr int NST = K / DXS;                     // weight stages per chunk
+  static_assert(K % DXS == 0, "taps per stage must divide K");
+  static constexpr size_t SMEM = sizeof(float) * (2 * ABUF * A_FLOATS + 2 * NBUF * B_STAGE_FLOATS) + 128 + 256;   // + barriers + bias
   static constexpr int ACC_COLS = 2 * R * NP;             // main + cross-term accumulators
   static constexpr int TMEM_COLS = (ACC_COLS <= 32) ? 32 : (ACC_COLS <= 64) ? 64 : (ACC_COLS <= 128) ? 128 : (ACC_COLS <= 256) ? 256 : 512;
   static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
   static_assert(TMEM_COLS * MINB <= 512, "TMEM oversubscribed");
   static_assert((R < K ? R : K) * NP <= 256, "MMA N exceeds 256");
-  static_assert((NBUF & (NBUF - 1)) == 0 && NBUF >= 2, "NBUF must be a power of two");
+  static_assert(NBUF >= 2 && NBUF <= 6 && (ABUF == 1 || ABUF == 2), "ring depths");
   static constexpr int A_TOTAL = ROWS * KG * PW;          // float4 elements staged per chunk
   static constexpr int STAGERS = TC_THREADS - 32;         // warp 0 only issues MMAs / weight fetches; warps 1..7 stage inputs
   static constexpr int A_ITER = (A_TOTAL + STAGERS - 1) / STAGERS;
@@ -156,24 +162,23 @@ __device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
 __device__ long long g_tc_trace[16];
 #ifdef RISP_TC_TRACE
 #define TC_TRACE(slot) do { if (trace_cta && tid == 0) g_tc_trace[slot] = clock64(); } while (0)
-#define TC_TRACE_ADD(slot, t_begin) do { if (trace_cta) g_tc_trace[slot] += clock64() - (t_begin); } while (0)
+#define TC_TRACE_ADD(slot, t_begin) do { tacc[slot - 8] += clock64() - (t_begin); } while (0)
 #else
 #define TC_TRACE(slot) do { } while (0)
 #define TC_TRACE_ADD(slot, t_begin) do { } while (0)
 #endif
 
-template <int K, int CI_C, int R, int NP, int NBUF, int MINB>
+template <int K, int CI_C, int R, int NP, int NBUF, int MINB, int ABUF, int PF, int DXS>
 __global__ void __launch_bounds__(TC_THREADS, MINB)
 conv_tc_kernel(ConvTcArgs a) {
-  using C = TcCfg<K, CI_C, R, NP, NBUF, MINB>;
+  using C = TcCfg<K, CI_C, R, NP, NBUF, MINB, ABUF, PF, DXS>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* sA_hi = reinterpret_cast<float*>(smem_raw);
-  float* sA_lo = sA_hi + C::A_FLOATS;
-  float* sB = sA_lo + C::A_FLOATS;                         // [buf][hi|lo][B_STAGE_FLOATS]
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(sB + 2 * NBUF * C::B_STAGE_FLOATS);   // bfull[NBUF], mdone[NBUF], afree
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2 * NBUF + 1);
+  float* sA = reinterpret_cast<float*>(smem_raw);          // [abuf][hi|lo][A_FLOATS]
+  float* sB = sA + 2 * ABUF * C::A_FLOATS;                 // [buf][hi|lo][B_STAGE_FLOATS]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sB + 2 * NBUF * C::B_STAGE_FLOATS);   // bfull[NBUF], mdone[NBUF], afree[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2 * NBUF + 2);
   float* s_bias = reinterpret_cast<float*>(mbar + 16);     // 64 floats, zero beyond Cout / without a bias
-  const uint32_t bfull = smem_u32(mbar), mdone = smem_u32(mbar + NBUF), afree = smem_u32(mbar + 2 * NBUF);
+  const uint32_t bfull = smem_u32(mbar), mdone = smem_u32(mbar + NBUF), afree = smem_u32(mbar + 2 * NBUF);   // afree[2]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int strips = (a.W + TC_M - 1) / TC_M;
@@ -185,6 +190,7 @@ conv_tc_kernel(ConvTcArgs a) {
   const bool trace_cta = blockIdx.x == 5 && blockIdx.y == 0;
   if (trace_cta && tid == 0) { for (int i = 0; i < 16; ++i) g_tc_trace[i] = 0; }
   long long tq = 0; (void)tq;
+  long long tacc[6] = {0, 0, 0, 0, 0, 0};      // per-thread accumulators (registers): slots 8..13
 #endif
   TC_TRACE(0);
 
@@ -194,7 +200,7 @@ conv_tc_kernel(ConvTcArgs a) {
   }
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < 2 * NBUF + 1; ++i) mbar_init(smem_u32(mbar + i), 1);
+    for (int i = 0; i < 2 * NBUF + 2; ++i) mbar_init(smem_u32(mbar + i), 1);
   }
   if (tid >= 64 && tid < 128) s_bias[tid - 64] = (a.bias && tid - 64 < a.Cout) ? __ldg(a.bias + tid - 64) : 0.f;
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -214,7 +220,7 @@ conv_tc_kernel(ConvTcArgs a) {
   // weight stage s -> buffer s % NBUF (hi block then lo block); issued by the MMA lane only
   auto fetch_weights = [&](int s) {
     const long long off = (long long)s * C::B_STAGE_FLOATS;              // stages are contiguous: [chunk][dx]
-    const uint32_t b = (uint32_t)(s & (NBUF - 1));
+    const uint32_t b = (uint32_t)(s % NBUF);
     const uint32_t bar = bfull + 8u * b;
     const uint32_t dst = smem_u32(sB) + b * 2u * kStageBytes;
     mbar_expect_tx(bar, 2u * kStageBytes);
@@ -225,7 +231,7 @@ conv_tc_kernel(ConvTcArgs a) {
   // input rows of chunk c -> registers (zero padding; the optional mask is applied here so only one array stays live).
   // The unmasked path must not contain any use of the loaded values: a (predicated-off) select right behind a load
   // still waits for it and would serialise the L2 latency of every element.
-  float4 v[C::A_ITER];
+  float4 va[C::A_ITER], vb[PF == 2 ? C::A_ITER : 1];
   auto input_offset = [&](int it, int c, long long& o) -> bool {
     const int i = (tid - 32) + it * C::STAGERS;
     const int px = i % C::PW;
@@ -235,7 +241,7 @@ conv_tc_kernel(ConvTcArgs a) {
     o = (long long)gy * row_stride + ((long long)gkg * a.W + gx) * 4;
     return i < C::A_TOTAL && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && gkg < a.CinG;
   };
-  auto load_inputs = [&](int c) {
+  auto load_set = [&](int c, float4* v) {
     if (warp == 0) return;
     if (!min_) {
 #pragma unroll
@@ -268,8 +274,10 @@ conv_tc_kernel(ConvTcArgs a) {
       }
     }
   };
-  auto store_inputs = [&]() {
+  auto store_set = [&](int c, const float4* v) {
     if (warp == 0) return;
+    float* sA_hi = sA + (size_t)(c % ABUF) * 2 * C::A_FLOATS;
+    float* sA_lo = sA_hi + C::A_FLOATS;
 #pragma unroll
     for (int it = 0; it < C::A_ITER; ++it) {
       const int i = (tid - 32) + it * C::STAGERS;
@@ -287,6 +295,10 @@ conv_tc_kernel(ConvTcArgs a) {
     }
   };
 
+  // register set of chunk c: alternating with PF = 2
+  auto load_inputs = [&](int c) { if (PF == 2 && (c & 1)) load_set(c, vb); else load_set(c, va); };
+  auto store_inputs = [&](int c) { if (PF == 2 && (c & 1)) store_set(c, vb); else store_set(c, va); };
+
   // ---- prologue: first weight stages in flight, accumulators zeroed, inputs of chunk 0 staged ----
   if (warp == 0) {
     if (elect_one()) {
@@ -296,6 +308,7 @@ conv_tc_kernel(ConvTcArgs a) {
   }
   TC_TRACE(5);
   load_inputs(0);
+  if (PF == 2 && n_chunks > 1) load_inputs(1);
   TC_TRACE(6);
   {
     // warp w owns TMEM lanes 32*(w%4)..; the two warp sets split the 16-column groups
@@ -306,7 +319,7 @@ conv_tc_kernel(ConvTcArgs a) {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
   TC_TRACE(7);
-  store_inputs();
+  store_inputs(0);
   TC_TRACE(14);
   fence_async_smem();        // generic-proxy smem writes -> visible to the tensor-core (async) proxy
   tc_fence_before();
@@ -314,30 +327,31 @@ conv_tc_kernel(ConvTcArgs a) {
   TC_TRACE(1);
 
   for (int s = 0; s < n_stages; ++s) {
-    const int c = s / C::NST, dx = s % C::NST;
+    const int c = s / C::NST, dx = s % C::NST;      // dx: stage within the chunk (DXS horizontal taps each)
     if (dx == 0 && s > 0) {
-      // chunk boundary: the MMAs of chunk c-1 (the only readers of the input tile) must have committed
+      // chunk boundary
 #ifdef RISP_TC_TRACE
       tq = clock64();
 #endif
-      mbar_wait(afree, (uint32_t)((c - 1) & 1));
-      if (tid == 0) TC_TRACE_ADD(8, tq);
+      // the previous reader of this chunk's input buffer is chunk c - ABUF
+      if (c >= ABUF) mbar_wait(afree + 8u * (uint32_t)(c % ABUF), (uint32_t)(((c - ABUF) / ABUF) & 1));
+      TC_TRACE_ADD(8, tq);
 #ifdef RISP_TC_TRACE
       tq = clock64();
 #endif
-      store_inputs();          // registers were loaded while those MMAs ran
-      if (tid == 0) TC_TRACE_ADD(12, tq);
+      store_inputs(c);         // registers were loaded while the MMAs ran
+      TC_TRACE_ADD(12, tq);
 #ifdef RISP_TC_TRACE
       tq = clock64();
 #endif
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
-      if (tid == 0) TC_TRACE_ADD(13, tq);
+      TC_TRACE_ADD(13, tq);
     }
     if (warp == 0) {
       if (elect_one()) {
-        const uint32_t b = (uint32_t)(s & (NBUF - 1));
+        const uint32_t b = (uint32_t)(s % NBUF);
 #ifdef RISP_TC_TRACE
         tq = clock64();
 #endif
@@ -348,11 +362,14 @@ conv_tc_kernel(ConvTcArgs a) {
 #endif
         tc_fence_after();
         const uint32_t sBh = smem_u32(sB) + b * 2u * kStageBytes, sBl = sBh + kStageBytes;
-        const uint32_t a_dx = (uint32_t)(dx * 16);
+        const uint32_t sAh = smem_u32(sA) + (uint32_t)(c % ABUF) * (uint32_t)(2 * C::A_FLOATS * 4), sAl = sAh + (uint32_t)(C::A_FLOATS * 4);
+#pragma unroll
+        for (int dxl = 0; dxl < DXS; ++dxl) {
+        const uint32_t a_dx = (uint32_t)((dx * DXS + dxl) * 16);
+        const uint32_t b_tap = (uint32_t)(dxl * C::B_TAP_FLOATS * 4);
 #pragma unroll
         for (int i = 0; i < C::ROWS; ++i) {
-          // input row i feeds output rows r_lo..r_hi; their weights are the column blocks j0.. of the stage
-          constexpr int dummy = 0; (void)dummy;
+          // input row i feeds output rows r_lo..r_hi; their weights are the column blocks j0.. of the tap
           const int r_lo = (i - K + 1 > 0) ? i - K + 1 : 0;
           const int r_hi = (i < R - 1) ? i : R - 1;
           const int nrows = r_hi - r_lo + 1;
@@ -363,9 +380,9 @@ conv_tc_kernel(ConvTcArgs a) {
 #pragma unroll
           for (int ks = 0; ks < C::KG / 2; ++ks) {
             const uint32_t a_off = (uint32_t)(i * C::A_ROW_FLOATS * 4 + (2 * ks) * C::PW * 16) + a_dx;
-            const uint32_t b_off = (uint32_t)((2 * ks) * C::NSTACK * 16 + j0 * NP * 16);
-            const uint64_t dAh = make_desc(smem_u32(sA_hi) + a_off, C::PW * 16, 128);
-            const uint64_t dAl = make_desc(smem_u32(sA_lo) + a_off, C::PW * 16, 128);
+            const uint32_t b_off = b_tap + (uint32_t)((2 * ks) * C::NSTACK * 16 + j0 * NP * 16);
+            const uint64_t dAh = make_desc(sAh + a_off, C::PW * 16, 128);
+            const uint64_t dAl = make_desc(sAl + a_off, C::PW * 16, 128);
             const uint64_t dBh = make_desc(sBh + b_off, C::NSTACK * 16, 128);
             const uint64_t dBl = make_desc(sBl + b_off, C::NSTACK * 16, 128);
             umma_tf32(d_main, dAh, dBh, idesc, 1u);
@@ -373,26 +390,31 @@ conv_tc_kernel(ConvTcArgs a) {
             umma_tf32(d_cross, dAh, dBl, idesc, 1u);
           }
         }
+        }
         umma_commit(mdone + 8u * b);
-        if (dx == C::NST - 1) umma_commit(afree);            // one phase per chunk (and the last one gates the epilogue)
+        if (dx == C::NST - 1) umma_commit(afree + 8u * (uint32_t)(c % ABUF));   // one phase per chunk and input buffer
         TC_TRACE_ADD(10, tq);
 #ifdef RISP_TC_TRACE
         tq = clock64();
 #endif
         const int sn = s + NBUF - 1;                          // refill the buffer stage s-1 used
         if (sn < n_stages) {
-          if (s >= 1) mbar_wait(mdone + 8u * (uint32_t)(sn & (NBUF - 1)), (uint32_t)(((s - 1) / NBUF) & 1));
+          if (s >= 1) mbar_wait(mdone + 8u * (uint32_t)(sn % NBUF), (uint32_t)(((s - 1) / NBUF) & 1));
           fetch_weights(sn);
         }
         TC_TRACE_ADD(11, tq);
       }
       __syncwarp();
     }
-    if (dx == 0 && c + 1 < n_chunks) load_inputs(c + 1);   // next chunk's rows: in flight while this chunk's MMAs run
+    if (dx == 0 && c + PF < n_chunks) load_inputs(c + PF);   // rows PF chunks ahead: in flight while the MMAs run
   }
   // ---- epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).., and the (w/4)-th half of the 16-column groups ----
   TC_TRACE(2);
-  mbar_wait(afree, (uint32_t)((n_chunks - 1) & 1));
+#ifdef RISP_TC_TRACE
+  if (trace_cta && warp == 0 && tacc[2] != 0) { g_tc_trace[9] = tacc[1]; g_tc_trace[10] = tacc[2]; g_tc_trace[11] = tacc[3]; }
+  if (trace_cta && tid == 32) { g_tc_trace[8] = tacc[0]; g_tc_trace[12] = tacc[4]; g_tc_trace[13] = tacc[5]; }
+#endif
+  mbar_wait(afree + 8u * (uint32_t)((n_chunks - 1) % ABUF), (uint32_t)(((n_chunks - 1) / ABUF) & 1));
   tc_fence_after();
   TC_TRACE(3);
   const bool relu_out = (a.flags & RISP_CONV_RELU_OUT) != 0, add_res = (a.flags & RISP_CONV_ADD_RES) != 0,
@@ -515,20 +537,20 @@ __global__ void from_blocked_kernel(const float* __restrict__ src, float* __rest
   }
 }
 
-template <int K, int CI_C, int R, int NP, int NBUF, int MINB>
+template <int K, int CI_C, int R, int NP, int NBUF, int MINB, int ABUF, int PF, int DXS>
 static int launch_tc(const ConvTcArgs& a, int N, cudaStream_t st) {
-  using C = TcCfg<K, CI_C, R, NP, NBUF, MINB>;
+  using C = TcCfg<K, CI_C, R, NP, NBUF, MINB, ABUF, PF, DXS>;
   static_assert(C::SMEM <= 227 * 1024 / MINB - 1024 * (MINB > 1), "shared memory budget");
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(conv_tc_kernel<K, CI_C, R, NP, NBUF, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_tc_kernel<K, CI_C, R, NP, NBUF, MINB, ABUF, PF, DXS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess) {
       set_error("conv_tc: cannot opt in to %zu bytes of shared memory", C::SMEM);
       return RISP_E_CUDA;
     }
     attr = true;
   }
   dim3 grid((unsigned)(cdiv(a.W, TC_M) * cdiv(a.H, R)), (unsigned)N);
-  conv_tc_kernel<K, CI_C, R, NP, NBUF, MINB><<<grid, TC_THREADS, C::SMEM, st>>>(a);
+  conv_tc_kernel<K, CI_C, R, NP, NBUF, MINB, ABUF, PF, DXS><<<grid, TC_THREADS, C::SMEM, st>>>(a);
   return check_launch("conv_tc_kernel");
 }
 
@@ -587,18 +609,19 @@ extern "C" int risp_conv_tc_fwd(const float* x_blk, const float* mask_in_blk, co
   const int NP = (Cout + 15) / 16 * 16;
   ConvTcArgs a{x_blk, wprep, bias, res_blk, mask_in_blk, mask_out_blk, y_blk, y_planar, risp_conv_tc_padded_channels(Cin) / 4, Cout, NP, H, W, flags};
   cudaStream_t st = as_stream(stream);
-#define RISP_TC(KK, RR, NN, BB, MM) return launch_tc<KK, 8, RR, NN, BB, MM>(a, N, st)
+#define RISP_TC(KK, RR, NN, BB, MM, AA, PP, DD) return launch_tc<KK, 8, RR, NN, BB, MM, AA, PP, DD>(a, N, st)
   // R rows per CTA: the fattest MMA has N = min(R,K)*NP <= 256; TMEM columns = 2*R*NP per CTA.  MM = 2 CTAs per SM
-  // where 2*R*NP <= 256 and shared memory <= ~112 KB, otherwise one CTA with twice the rows.  BB = weight-stage ring depth.
+  // where 2*R*NP <= 256 and shared memory <= 112.5 KB, otherwise one CTA with more rows.  BB = weight-stage ring depth,
+  // AA = input-tile buffers, PP = chunks prefetched in registers, DD = horizontal taps per weight stage.
   switch (K) {
     case 1:
-      switch (NP) { case 16: RISP_TC(1, 8, 16, 4, 2); case 32: RISP_TC(1, 4, 32, 4, 2); case 48: RISP_TC(1, 2, 48, 4, 2); default: RISP_TC(1, 2, 64, 4, 2); }
+      switch (NP) { case 16: RISP_TC(1, 8, 16, 4, 2, 1, 1, 1); case 32: RISP_TC(1, 4, 32, 4, 2, 2, 2, 1); case 48: RISP_TC(1, 2, 48, 4, 2, 2, 2, 1); default: RISP_TC(1, 2, 64, 4, 2, 2, 2, 1); }
     case 3:
-      switch (NP) { case 16: RISP_TC(3, 8, 16, 4, 2); case 32: RISP_TC(3, 4, 32, 4, 2); case 48: RISP_TC(3, 2, 48, 4, 2); default: RISP_TC(3, 2, 64, 4, 2); }
+      switch (NP) { case 16: RISP_TC(3, 8, 16, 2, 2, 1, 1, 3); case 32: RISP_TC(3, 4, 32, 2, 2, 1, 2, 3); case 48: RISP_TC(3, 2, 48, 2, 2, 1, 2, 3); default: RISP_TC(3, 2, 64, 2, 2, 1, 2, 3); }
     case 5:
-      switch (NP) { case 16: RISP_TC(5, 4, 16, 4, 2); case 32: RISP_TC(5, 4, 32, 4, 2); case 48: RISP_TC(5, 2, 48, 2, 2); default: RISP_TC(5, 2, 64, 2, 2); }
+      switch (NP) { case 16: RISP_TC(5, 4, 16, 4, 2, 1, 1, 1); case 32: RISP_TC(5, 4, 32, 4, 2, 1, 1, 1); case 48: RISP_TC(5, 2, 48, 2, 2, 1, 1, 1); default: RISP_TC(5, 2, 64, 2, 2, 1, 1, 1); }
     default:
-      switch (NP) { case 16: RISP_TC(9, 8, 16, 4, 1); case 32: RISP_TC(9, 4, 32, 2, 1); case 48: RISP_TC(9, 4, 48, 2, 1); default: RISP_TC(9, 4, 64, 2, 1); }
+      switch (NP) { case 16: RISP_TC(9, 8, 16, 4, 1, 1, 1, 1); case 32: RISP_TC(9, 4, 32, 2, 1, 1, 1, 1); case 48: RISP_TC(9, 4, 48, 2, 1, 1, 1, 1); default: RISP_TC(9, 4, 64, 2, 1, 1, 1, 1); }
   }
 #undef RISP_TC
 }

@@ -3,7 +3,7 @@ import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from reconfigisp_b200 import ops, _lib as L
-for Cin, Cout, K in ((15, 64, 9), (64, 15, 9), (64, 64, 3), (64, 32, 5)):
+for Cin, Cout, K in ((64, 64, 3), (15, 64, 9), (64, 32, 5)):
     x = torch.randn(4, Cin, 256, 256, device='cuda'); w = torch.randn(Cout, Cin, K, K, device='cuda') * 0.05; b = torch.randn(Cout, device='cuda')
     xb = ops.to_blocked(x)
     for _ in range(3):
@@ -12,7 +12,7 @@ for Cin, Cout, K in ((15, 64, 9), (64, 15, 9), (64, 64, 3), (64, 32, 5)):
     out = (ctypes.c_longlong * 16)()
     L.call('risp_debug_tc_trace', out)
     t = list(out)
-    print('   prologue detail: setup %d  load-issue %d  tmem-zero %d  store %d  fence+sync %d ; boundaries: store %d  fence+sync %d' % (
+    print('   prologue detail: setup %d  load-issue %d  tmem-zero %d  store %d  fence+sync %d ; boundaries (a stager thread): store %d  fence+sync-wait %d' % (
         t[5] - t[0], t[6] - t[5], t[7] - t[6], t[14] - t[7], t[1] - t[14], t[12], t[13]))
     print('%2d->%2d k%d: prologue %d | stage loop %d | drain %d | epilogue %d | total %d ;  boundary-wait %d  weight-wait %d  issue %d  refill %d' % (
         Cin, Cout, K, t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[4] - t[0], t[8], t[9], t[10], t[11]), flush=True)
