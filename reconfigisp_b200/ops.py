@@ -337,14 +337,16 @@ def bayer_blc_wb(raw, params):
     return _BlcWbFn.apply(raw, params)
 
 
-def decode_codes(codes, denom):
+def decode_codes(codes, denom, out=None):
     """uint8 / uint16 (or int16) codes on the device -> fp32 codes/denom (the loaders' /255., /1023., /16383.)."""
     if not codes.is_cuda:
         raise RuntimeError('decode_codes runs on CUDA tensors only')
     codes = codes.contiguous()
     nbytes = codes.element_size()
     assert nbytes in (1, 2) and not codes.dtype.is_floating_point
-    out = torch.empty(codes.shape, device=codes.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty(codes.shape, device=codes.device, dtype=torch.float32)
+    assert out.shape == codes.shape and out.dtype == torch.float32 and out.is_contiguous()
     L.call('risp_decode_codes', L.ptr(codes), L.ptr(out), codes.numel(), nbytes, float(denom), L.stream())
     return out
 

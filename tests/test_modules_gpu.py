@@ -206,3 +206,32 @@ def test_plugin_boundary_run_signatures():
     assert maxabs(out.permute(0, 3, 1, 2) / 255, O.denoise_fastnlm(x * 255, win, [5, 3], [20., 50.]) / 255) <= 1e-4
     with pytest.raises(ValueError):
         gamma.Gamma().run(nhwc, 'auto', {})
+
+
+def test_tuning_step_cuda_graph_matches_eager():
+    """IspModel replays the fused tuning step from a CUDA graph; parameters after several steps must match the
+    eagerly launched step (same kernels, same order), also when new data is fed into the persistent buffers."""
+    from reconfigisp_b200.tuning import IspModel
+    from reconfigisp_b200.synthetic import synthetic_frames
+
+    def opt(graph):
+        return {'model': 'isp', 'is_train': True, 'cuda_graph': graph,
+                'network_G': {'which_model_G': 'OriginUniversal', 'architecture': 'Bayer_02_Demosaic_02_sRGB_11_13_01_14', 'weight_seed': 10},
+                'train': {'lr_G': 1e-2, 'beta1': 0.9, 'beta2': 0.99, 'pixel_criterion': 'l2', 'lr_scheme': 'MultiStepLR',
+                          'lr_steps': [1000], 'lr_gamma': 0.5}, 'path': {'pretrain_model_G': None}}
+    raw, gt = synthetic_frames(4, 64, 96, seed=3)
+    raw_c, gt_c = torch.round(raw * 1023).to(torch.int16), torch.round(gt * 255).to(torch.uint8)
+    models = [IspModel(opt(True)), IspModel(opt(True))]
+    models[0].use_graph = False          # same (capturable) Adam arithmetic, launched eagerly
+    losses = [[], []]
+    for k, m in enumerate(models):
+        for step in range(8):
+            sl = slice(0, 2) if step % 2 == 0 else slice(2, 4)
+            m.feed_data((raw_c[sl], gt_c[sl]) if step >= 6 else (raw[sl], gt[sl]))
+            m.optimize_parameters()
+            losses[k].append(float(m.log_dict['loss']))
+    assert models[1]._graph is not None, 'the graph path was not taken'
+    assert max(abs(a - b) for a, b in zip(*losses)) <= 1e-6 * max(losses[0]), losses
+    for pa, pb in zip(models[0].netG.trainable_parameters, models[1].netG.trainable_parameters):
+        if pa.numel():
+            assert maxabs(pa, pb.detach()) <= 1e-5
