@@ -223,7 +223,7 @@ def run_b200(args):
                 'e2e_codec': {'value': round(e2e_codec, 1), 'unit': 'MP/s', 'h2d_bytes_per_step': 5 * px_per_step_rank,
                               'd2h_bytes_per_step': 4, 'ms_per_step': round(ms_codec, 3),
                               'note': 'same step; raw as 10-bit codes (int16) and GT as uint8 cross PCIe, normalised on the device'},
-                'gpu_launches': 3 * args.steps,
+                'gpu_launches': 2 * args.steps,          # per step: risp::pipeline_kernel + risp::finalize_rows_kernel
                 'roofline': {'bound': 'hbm', 'achieved': round(achieved, 1), 'peak': peak, 'unit': 'GB/s',
                              'frac': round(achieved / peak, 4), 'traffic': None, 'kernel': 'risp::pipeline_kernel<BILINEAR, STEP, sigA>',
                              'ms_per_launch': round(ms_k, 4), 'algorithmic_bytes_per_px': ALGO_BYTES_PER_PX}}

@@ -119,6 +119,82 @@ int finalize_partials(const float* partial, float* out, int R, int B, int NS, in
   return check_launch("finalize_kernel");
 }
 
+// ---- two-level reduction in ONE launch (the tuning step's finaliser) ---------------------------------------
+// Level 1: kFinBlocks CTAs per output row each reduce a contiguous slice of partial rows for ALL slots at once (a warp
+// reads whole partial rows: coalesced), fixed warp order.  Level 2: the last CTA to finish (ticket counter) adds the
+// kFinBlocks slice sums in index order, applies the slot -> parameter map and the scales, zero-fills unmapped
+// parameters and (optionally) writes the loss.  Fixed summation order => bit-reproducible.
+__global__ void __launch_bounds__(256)
+finalize_rows_kernel(const float* __restrict__ partial, float* __restrict__ scratch, unsigned int* __restrict__ counter,
+                     float* __restrict__ out, float* __restrict__ loss_out, int R, int B, int NS, int P, SlotMap map,
+                     float scale, float loss_scale, int loss_slot, int sum_rows) {
+  __shared__ float s_part[8][64];
+  __shared__ float s_tot[64];
+  __shared__ int s_last;
+  const int rp = blockIdx.y, G = gridDim.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long rows_total = sum_rows ? (long long)R * B : B;
+  const long long base = sum_rows ? 0 : (long long)rp * B;
+  const long long per = (rows_total + G - 1) / G;
+  const long long lo = (long long)blockIdx.x * per, hi = (lo + per < rows_total) ? lo + per : rows_total;
+  float acc0 = 0.f, acc1 = 0.f;
+  for (long long row = lo + wid; row < hi; row += 8) {
+    const float* p = partial + (base + row) * NS;
+    acc0 += p[lane];
+    if (lane + 32 < NS) acc1 += p[lane + 32];
+  }
+  s_part[wid][lane] = acc0;
+  s_part[wid][lane + 32] = acc1;
+  __syncthreads();
+  if (threadIdx.x < NS) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_part[w][threadIdx.x];
+    scratch[((long long)rp * G + blockIdx.x) * NS + threadIdx.x] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(counter + rp, 1u) == (unsigned int)(G - 1));
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < NS) {
+    float t = 0.f;
+    for (int g = 0; g < G; ++g) t += __ldcg(scratch + ((long long)rp * G + g) * NS + threadIdx.x);
+    s_tot[threadIdx.x] = t;
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < P; q += blockDim.x) {
+    float v = 0.f;
+    for (int e = 0; e < map.n; ++e)
+      if (map.dst[e] == q) v = s_tot[map.slot[e]] * scale;
+    out[(long long)rp * P + q] = v;
+  }
+  if (loss_out && rp == 0 && threadIdx.x == 0) loss_out[0] = s_tot[loss_slot] * loss_scale;
+  if (threadIdx.x == 0) counter[rp] = 0;      // ready for the next launch on this workspace
+}
+
+size_t finalize_rows_workspace(int R, int NS) {
+  return ((size_t)R * kFinBlocks * NS + 64) * sizeof(float);     // slice sums + ticket counters
+}
+
+int finalize_rows(const float* partial, void* scratch_ws, float* out, float* loss_out, int R, int B, int NS, int P,
+                  const short* dst, const short* slot, int n, float scale, float loss_scale, int loss_slot, bool sum_rows,
+                  cudaStream_t st) {
+  RISP_REQUIRE(n <= 96 && NS <= 64 && R <= 64, RISP_E_INVALID, "finalize_rows: %d entries / %d slots / %d rows", n, NS, R);
+  SlotMap m;
+  m.n = n;
+  for (int i = 0; i < n; ++i) { m.dst[i] = dst[i]; m.slot[i] = slot[i]; }
+  float* scratch = static_cast<float*>(scratch_ws);
+  unsigned int* counter = reinterpret_cast<unsigned int*>(scratch + (size_t)R * kFinBlocks * NS);
+  const int Rp = sum_rows ? 1 : R;
+  // the ticket counters must be zero: the kernel re-arms them, but the workspace is caller-owned scratch
+  if (cudaMemsetAsync(counter, 0, sizeof(unsigned int) * Rp, st) != cudaSuccess) { set_error("finalize_rows: memset failed"); return RISP_E_CUDA; }
+  finalize_rows_kernel<<<dim3(kFinBlocks, Rp), 256, 0, st>>>(partial, scratch, counter, out, loss_out, R, B, NS, P, m, scale,
+                                                            loss_scale, loss_slot, sum_rows ? 1 : 0);
+  return check_launch("finalize_rows_kernel");
+}
+
 }  // namespace risp
 
 extern "C" {

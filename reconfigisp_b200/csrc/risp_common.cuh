@@ -106,4 +106,13 @@ void chain_slot_list(const ChainDesc& d, SlotList* m);
 int finalize_partials(const float* partial, float* out, int R, int B, int NS, int P, const short* dst,
                       const short* slot, int n, float scale, bool sum_rows, cudaStream_t st);
 
+// Same reduction for many slots at once, two levels in one launch (see risp_api.cu).  `scratch_ws` holds
+// finalize_rows_workspace(R, NS) bytes.  Writes ALL P entries of every output row (unmapped ones become 0) and, when
+// loss_out is given (sum_rows only), loss_out[0] = loss_scale * sum(partial[..][loss_slot]).
+constexpr int kFinBlocks = 64;
+size_t finalize_rows_workspace(int R, int NS);
+int finalize_rows(const float* partial, void* scratch_ws, float* out, float* loss_out, int R, int B, int NS, int P,
+                  const short* dst, const short* slot, int n, float scale, float loss_scale, int loss_slot, bool sum_rows,
+                  cudaStream_t st);
+
 }  // namespace risp

@@ -380,7 +380,7 @@ extern "C" size_t risp_pipeline_step_workspace(int N, int H, int W, int P) {
   (void)P;
   if (N <= 0 || H <= 0 || W <= 0) return 0;
   PipeGeom g = pipe_geometry(N, H, W);
-  return (size_t)N * g.warps_per_image * RISP_NSLOT * sizeof(float);
+  return (size_t)N * g.warps_per_image * RISP_NSLOT * sizeof(float) + finalize_rows_workspace(N, RISP_NSLOT);
 }
 
 static int pipeline_step_impl(const char* who, bool gt_is_dy, const float* raw, const float* gt, float* y_out,
@@ -412,22 +412,38 @@ static int pipeline_step_impl(const char* who, bool gt_is_dy, const float* raw, 
   rc = launch_pipeline<MODE_STEP>(a, d, N, dm_kind, big, st);
   if (rc != RISP_OK) return rc;
   const double numel = (double)N * 3.0 * H * W;
-  if (!gt_is_dy) {
+  const bool shared_row = (param_stride == 0);
+  void* fin_ws = partial + (size_t)N * g.warps_per_image * RISP_NSLOT;
+  if (N > 64 || P == 0) {
+    // rare shapes: the one-warp-per-entry finaliser
+    if (!gt_is_dy) {
+      const short loss_dst = 0, loss_slot = RISP_SLOT_LOSS;
+      rc = finalize_partials(partial, loss_out, N, g.warps_per_image, RISP_NSLOT, 1, &loss_dst, &loss_slot, 1,
+                             (float)(1.0 / numel), true, st);
+      if (rc != RISP_OK) return rc;
+    }
+    if (P == 0) return RISP_OK;
+    if (cudaMemsetAsync(dparams, 0, sizeof(float) * (size_t)P * (shared_row ? 1 : N), st) != cudaSuccess) {
+      set_error("%s: memset failed", who);
+      return RISP_E_CUDA;
+    }
+    SlotList m;
+    chain_slot_list(d, &m);
+    return finalize_partials(partial, dparams, N, g.warps_per_image, RISP_NSLOT, P, m.dst, m.slot, m.n,
+                             gt_is_dy ? 1.f : (float)(2.0 / numel), shared_row, st);
+  }
+  // loss and every parameter gradient in one launch (the loss rides along when all frames share one parameter row)
+  const bool loss_inline = !gt_is_dy && shared_row;
+  if (!gt_is_dy && !loss_inline) {
     const short loss_dst = 0, loss_slot = RISP_SLOT_LOSS;
     rc = finalize_partials(partial, loss_out, N, g.warps_per_image, RISP_NSLOT, 1, &loss_dst, &loss_slot, 1,
                            (float)(1.0 / numel), true, st);
     if (rc != RISP_OK) return rc;
   }
-  if (P == 0) return RISP_OK;
-  bool shared_row = (param_stride == 0);
-  if (cudaMemsetAsync(dparams, 0, sizeof(float) * (size_t)P * (shared_row ? 1 : N), st) != cudaSuccess) {
-    set_error("%s: memset failed", who);
-    return RISP_E_CUDA;
-  }
   SlotList m;
   chain_slot_list(d, &m);
-  return finalize_partials(partial, dparams, N, g.warps_per_image, RISP_NSLOT, P, m.dst, m.slot, m.n,
-                           gt_is_dy ? 1.f : (float)(2.0 / numel), shared_row, st);
+  return finalize_rows(partial, fin_ws, dparams, loss_inline ? loss_out : nullptr, N, g.warps_per_image, RISP_NSLOT, P, m.dst,
+                       m.slot, m.n, gt_is_dy ? 1.f : (float)(2.0 / numel), (float)(1.0 / numel), RISP_SLOT_LOSS, shared_row, st);
 }
 
 extern "C" int risp_pipeline_mse_step(const float* raw, const float* gt, float* y_out, float* loss_out, float* dparams,
