@@ -94,17 +94,27 @@ struct SlotMap {
   short slot[96];
 };
 
-__global__ void finalize_kernel(const float* __restrict__ partial, float* __restrict__ out, int R, int B, int NS,
-                                int P, SlotMap map, float scale, int sum_rows) {
-  int e = blockIdx.x;
-  int r = blockIdx.y;
-  int lane = threadIdx.x;
+__global__ void __launch_bounds__(256)
+finalize_kernel(const float* __restrict__ partial, float* __restrict__ out, int R, int B, int NS,
+                int P, SlotMap map, float scale, int sum_rows) {
+  // one CTA per entry: 256 rows in flight (each thread walks its own rows: fixed assignment), then a fixed-order
+  // tree over warps -- deterministic, and the row loads overlap instead of queueing behind one warp
+  __shared__ float s_w[8];
+  const int e = blockIdx.x, r = blockIdx.y;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long rows = sum_rows ? (long long)R * B : B;
+  const float* p = partial + (sum_rows ? 0 : (long long)r * B) * NS + map.slot[e];
   float acc = 0.f;
-  int r0 = sum_rows ? 0 : r, r1 = sum_rows ? R : r + 1;
-  for (int rr = r0; rr < r1; ++rr)
-    for (int b = lane; b < B; b += 32) acc += partial[((long long)rr * B + b) * NS + map.slot[e]];
+  for (long long b = threadIdx.x; b < rows; b += 256) acc += p[b * NS];
   acc = warp_sum(acc);
-  if (lane == 0) out[(long long)(sum_rows ? 0 : r) * P + map.dst[e]] = acc * scale;
+  if (lane == 0) s_w[wid] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_w[w];
+    out[(long long)(sum_rows ? 0 : r) * P + map.dst[e]] = t * scale;
+  }
 }
 
 int finalize_partials(const float* partial, float* out, int R, int B, int NS, int P, const short* dst,
@@ -115,7 +125,7 @@ int finalize_partials(const float* partial, float* out, int R, int B, int NS, in
   m.n = n;
   for (int i = 0; i < n; ++i) { m.dst[i] = dst[i]; m.slot[i] = slot[i]; }
   dim3 grid(n, sum_rows ? 1 : R);
-  finalize_kernel<<<grid, 32, 0, st>>>(partial, out, R, B, NS, P, m, scale, sum_rows ? 1 : 0);
+  finalize_kernel<<<grid, 256, 0, st>>>(partial, out, R, B, NS, P, m, scale, sum_rows ? 1 : 0);
   return check_launch("finalize_kernel");
 }
 
