@@ -242,8 +242,15 @@ def run_b200(args):
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
+        # teardown must never hold the job: release the captured graphs first, and leave hard if NCCL teardown stalls
+        model._graph = None
+        torch.cuda.synchronize()
+        watchdog = threading.Timer(60.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
         dist.barrier()
         dist.destroy_process_group()
+        watchdog.cancel()
     return 0
 
 

@@ -108,7 +108,11 @@ class IspModel:
     def _graph_replay(self):
         key = self._graph_signature()
         if self._graph is not None and key == self._graph_key:
-            self._graph.replay()
+            g_loss, g_update = self._graph
+            g_loss.replay()
+            if g_update is not None:                       # data parallel: the collective stays outside the graphs
+                self._allreduce_grads()
+                g_update.replay()
             self.log_dict['loss'] = self.l_pix
             return True
         self._graph = None
@@ -120,36 +124,49 @@ class IspModel:
             return False
         try:
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._step_eager(count=False)
-            self._graph, self._graph_key = g, key          # the capture itself does not execute the step ...
-            g.replay()                                     # ... so run it once now
-            self.log_dict['loss'] = self.l_pix
-            return True
+            g_loss, g_update = torch.cuda.CUDAGraph(), None
+            if not D.is_dist():
+                with torch.cuda.graph(g_loss):
+                    self._step_eager(count=False)
+            else:
+                # NCCL kernels are kept out of the graphs (a captured collective ties the communicator's lifetime to
+                # the graph's): [table, pipeline kernel, finaliser, backward] | all-reduce | [Adam]
+                with torch.cuda.graph(g_loss):
+                    self._loss_and_grads()
+                g_update = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_update, pool=g_loss.pool()):
+                    self.optimizer_G.step()
+            self._graph, self._graph_key = (g_loss, g_update), key
+            return self._graph_replay()                    # capturing does not execute: run the step now
         except Exception as e:                             # capture is an optimisation: fall back to eager launches
             import logging
             logging.getLogger('base').warning('CUDA-graph capture of the tuning step failed (%s); running eagerly', e)
-            self.use_graph = False
+            self.use_graph, self._graph = False, None
             torch.cuda.synchronize()
             return False
 
-    def _step_eager(self, count=True):
-        if count:
-            self._eager_steps += 1
+    def _loss_and_grads(self):
         l_pix = self._fused_loss()
         if l_pix is None:
             self._output = self.netG(self.img)
             l_pix = (ops.l1_loss if self.loss_type == 'l1' else ops.mse_loss)(self._output, self.gt)
         self.optimizer_G.zero_grad()
         l_pix.backward()
+        self.l_pix = l_pix.detach()
+        self.log_dict['loss'] = self.l_pix             # device scalar; `.item()` it when logging
+
+    def _allreduce_grads(self):
         if D.is_dist():
             ps = [p for p in self.netG.trainable_parameters if p.grad is not None]
             for p, g in zip(ps, D.allreduce_mean_flat([p.grad for p in ps])):
                 p.grad.copy_(g)
+
+    def _step_eager(self, count=True):
+        if count:
+            self._eager_steps += 1
+        self._loss_and_grads()
+        self._allreduce_grads()
         self.optimizer_G.step()
-        self.l_pix = l_pix.detach()
-        self.log_dict['loss'] = self.l_pix             # device scalar; `.item()` it when logging
 
     @property
     def output(self):
