@@ -204,7 +204,11 @@ def run_b200(args):
     with torch.no_grad():
         table = model.netG._segment_table(keep, B).contiguous()
     ms_k = timed(lambda: step(model.img, model.gt, table), args.steps, args.warmup) / args.steps
-    clocks = sampler.summary()          # sampled across all timed legs (value, e2e, e2e_codec, roofline)
+    # ---- forward-only (fused inference, the other half of BASELINE.json's metric): read raw, write BGR = 16 B/px ----
+    with torch.no_grad():
+        ms_f = timed(lambda: ops.pipeline_fwd(model.img, dm_kind, chain, table), max(10, args.steps // 4), args.warmup) / max(10, args.steps // 4)
+    fwd_rate = world * px_per_step_rank / 1e6 / (ms_f / 1e3)
+    clocks = sampler.summary()          # sampled across all timed legs (value, e2e, e2e_codec, roofline, fwd)
     peak, peak_src = measured_peak_gbs()
     achieved = ALGO_BYTES_PER_PX * px_per_step_rank / (ms_k / 1e3) / 1e9
 
@@ -223,6 +227,9 @@ def run_b200(args):
                 'e2e_codec': {'value': round(e2e_codec, 1), 'unit': 'MP/s', 'h2d_bytes_per_step': 5 * px_per_step_rank,
                               'd2h_bytes_per_step': 4, 'ms_per_step': round(ms_codec, 3),
                               'note': 'same step; raw as 10-bit codes (int16) and GT as uint8 cross PCIe, normalised on the device'},
+                'fwd': {'value': round(fwd_rate, 1), 'unit': 'MP/s', 'ms_per_step': round(ms_f, 4),
+                        'roofline_frac': round(ALGO_BYTES_PER_PX * px_per_step_rank / (ms_f / 1e3) / 1e9 / measured_peak_gbs()[0], 4),
+                        'note': 'fused inference of the same pipeline (demosaic + 4 stages in one pass), data resident'},
                 'gpu_launches': 2 * args.steps,          # per step: risp::pipeline_kernel + risp::finalize_rows_kernel
                 'roofline': {'bound': 'hbm', 'achieved': round(achieved, 1), 'peak': peak, 'unit': 'GB/s',
                              'frac': round(achieved / peak, 4), 'traffic': None, 'kernel': 'risp::pipeline_kernel<BILINEAR, STEP, sigA>',
