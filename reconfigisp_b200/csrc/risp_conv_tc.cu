@@ -621,7 +621,7 @@ extern "C" int risp_conv_tc_fwd(const float* x_blk, const float* mask_in_blk, co
     case 5:
       switch (NP) { case 16: RISP_TC(5, 4, 16, 4, 2, 1, 1, 1); case 32: RISP_TC(5, 4, 32, 4, 2, 1, 1, 1); case 48: RISP_TC(5, 2, 48, 2, 2, 1, 1, 1); default: RISP_TC(5, 2, 64, 2, 2, 1, 1, 1); }
     default:
-      switch (NP) { case 16: RISP_TC(9, 8, 16, 4, 1, 1, 1, 1); case 32: RISP_TC(9, 4, 32, 2, 1, 1, 1, 1); case 48: RISP_TC(9, 4, 48, 2, 1, 1, 1, 1); default: RISP_TC(9, 4, 64, 2, 1, 1, 1, 1); }
+      switch (NP) { case 16: RISP_TC(9, 8, 16, 4, 1, 1, 1, 1); case 32: RISP_TC(9, 4, 32, 4, 1, 1, 1, 1); case 48: RISP_TC(9, 4, 48, 3, 1, 1, 1, 1); default: RISP_TC(9, 4, 64, 3, 1, 1, 1, 1); }
   }
 #undef RISP_TC
 }
