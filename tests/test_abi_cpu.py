@@ -94,3 +94,22 @@ def test_patch_origins_and_synthetic_data():
     assert torch.equal(torch.round(raw * 1023) / 1023, raw) and torch.equal(torch.round(gt * 255) / 255, gt)
     raw2, _ = synthetic_frames(2, 32, 48, seed=10)
     assert torch.equal(raw, raw2) and not torch.equal(raw[0], raw[1])
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints one JSON line with the contract's keys."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-500:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['unit'] == 'MP/s' and line['value'] > 0 and line['higher_is_better'] is True
+    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    assert line['e2e'] == {'value': line['value'], 'unit': 'MP/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert 'workload' in line['config'] and 'model' not in line['config']
+    # ranks other than 0 exit without work under torchrun
+    env = dict(os.environ, RANK='1', WORLD_SIZE='2', LOCAL_RANK='1')
+    r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--gpus', '2', '--steps', '1', '--warmup', '0'],
+                       capture_output=True, text=True, timeout=120, cwd=root, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ''
