@@ -113,3 +113,29 @@ def test_bench_reference_arm_line():
     r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--gpus', '2', '--steps', '1', '--warmup', '0'],
                        capture_output=True, text=True, timeout=120, cwd=root, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ''
+
+
+def test_header_is_plain_c_and_a_c_host_links():
+    """The boundary is a C ABI: the header must compile as C99 and as C++17, and a C program must link and run
+    against the shared library (no compute call: there is no GPU here)."""
+    import os, shutil, subprocess, tempfile
+    if shutil.which('gcc') is None:
+        pytest.skip('no gcc')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, 'reconfigisp_b200')
+    src = ('#include "reconfigisp_b200.h"\n#include <stdio.h>\n'
+           'int main(void) { size_t ws = risp_pipeline_step_workspace(4, 3000, 4000, 37);\n'
+           '  printf("%d %d %zu\\n", risp_abi_version(), risp_conv_tc_supported(64, 64, 3), ws);\n'
+           '  return (risp_chain_fwd(0, 0, 1, 16, 0, 0, 0, 0, 0, 0, 1.f, 1.f, 0) == RISP_OK) ? 1 : 0; }\n')
+    with tempfile.TemporaryDirectory() as d:
+        for ext, cc, std in (('c', 'gcc', '-std=c99'), ('cpp', 'g++', '-std=c++17')):
+            path = os.path.join(d, 't.' + ext)
+            open(path, 'w').write(src)
+            exe = os.path.join(d, 't_' + ext)
+            r = subprocess.run([cc, std, '-Wall', '-Werror', '-I', os.path.join(root, 'include'), path, '-L', libdir,
+                                '-lreconfigisp_b200', '-Wl,-rpath,' + libdir, '-o', exe], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+            r = subprocess.run([exe], capture_output=True, text=True)
+            assert r.returncode == 0, (r.stdout, r.stderr)           # null pointers are rejected with an error code
+            ver, tc, ws = r.stdout.split()
+            assert int(ver) >= 1 and int(tc) == 1 and int(ws) > 0
