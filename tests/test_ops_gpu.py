@@ -208,7 +208,7 @@ def test_fused_pipeline_fwd_and_step(ops, kind):
     pg = dev(params).requires_grad_()
     lg = ops.pipeline_mse(pg, dev(raw), dev(gt), kind, chain)
     dpg, = torch.autograd.grad(lg, pg)
-    assert abs(float(lg) - float(lo)) <= 1e-5 * max(1.0, float(lo))
+    assert abs(float(lg.detach()) - float(lo.detach())) <= 1e-5 * max(1.0, float(lo.detach()))
     relclose(dpg, dpo, rtol=2e-3, atol=1e-6)
     # per-image parameter rows
     pN = params.repeat(N, 1) * (1 + 0.01 * torch.arange(N).view(N, 1))
@@ -377,7 +377,7 @@ def test_loss(ops):
         yg = dev(y).requires_grad_()
         lg = fn(yg, dev(gt))
         dg, = torch.autograd.grad(lg * 3.0, yg)
-        assert abs(float(lg) - float(lo)) <= 1e-6
+        assert abs(float(lg.detach()) - float(lo.detach())) <= 1e-6
         assert maxabs(dg, do) <= 1e-7
 
 
@@ -475,7 +475,7 @@ def test_conv2d_tensor_core_path(ops, cfg):
             gg = torch.autograd.grad(yg, (xg, rg) if use_res else (xg,), dev(d))
             # the tensor core rounds its accumulator toward zero once per MMA: the error grows with the number of
             # chained MMAs (taps x channels / 8) and is RELATIVE to the accumulated magnitude
-            assert maxabs(yg, yo) <= 4e-5 * max(1.0, float(yo.abs().max())), (cfg, H, W, relu_in, relu_out, use_res, maxabs(yg, yo))
+            assert maxabs(yg, yo) <= 4e-5 * max(1.0, float(yo.detach().abs().max())), (cfg, H, W, relu_in, relu_out, use_res, maxabs(yg, yo))
             for a, bb in zip(gg, go):
                 err = (a.detach().cpu().double() - bb).abs()
                 tol = 1.5e-4 * max(1.0, float(bb.abs().max()))
