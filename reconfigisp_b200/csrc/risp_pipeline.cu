@@ -16,6 +16,8 @@
 #include "risp_common.cuh"
 #include "risp_stage.cuh"
 
+#include <stdlib.h>
+
 namespace risp {
 
 constexpr int kWarpsPerBlock = 4;
@@ -117,6 +119,12 @@ __device__ __forceinline__ void demosaic4(const float (&w)[2 * HL + 1][4 + 2 * H
 }
 
 enum { MODE_FWD = 0, MODE_STEP = 1 };
+
+// packed-fp32 / constant-bank kernels for the pre-instantiated signatures (risp_fused.cu)
+bool fused_handles(const ChainDesc& d, int N, int param_stride, int H, int W);
+int fused_partial_rows_per_frame(int N, int H, int W);
+int fused_launch(int mode, const float* raw, const float* gt, float* y, float* partial, const float* params, int pstride,
+                 int N, int H, int W, int dm_kind, float clip_hi, const ChainDesc& d, cudaStream_t st, int* rows_per_frame);
 
 struct PipeArgs {
   const float* raw;   // (N,1,H,W)
@@ -352,6 +360,13 @@ static int launch_pipeline(const PipeArgs& a, const ChainDesc& d, int N, int dm_
   return check_launch("pipeline_kernel");
 }
 
+// RISP_FUSED=0 in the environment keeps every chain on the interpreter-style kernels of this file (A/B measurements)
+static bool use_fused() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RISP_FUSED"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
 static int check_frame(const char* who, const void* raw, int N, int H, int W) {
   RISP_REQUIRE(raw && N > 0 && H >= 4 && W >= 4, RISP_E_INVALID, "%s: bad frame arguments", who);
   RISP_REQUIRE(H % 2 == 0 && W % 4 == 0, RISP_E_ALIGN, "%s: needs H even and W %% 4 == 0 (got %dx%d)", who, H, W);
@@ -376,6 +391,10 @@ extern "C" int risp_pipeline_fwd(const float* raw, float* y, int N, int H, int W
   if (rc != RISP_OK) return rc;
   RISP_REQUIRE(P == 0 || params, RISP_E_INVALID, "risp_pipeline_fwd: chain needs %d parameters but params is null", P);
   RISP_REQUIRE(param_stride == 0 || param_stride >= P, RISP_E_INVALID, "risp_pipeline_fwd: param_stride %d < %d", param_stride, P);
+  if (S > 0 && use_fused()) {
+    rc = fused_launch(0, raw, nullptr, y, nullptr, params, param_stride, N, H, W, dm_kind, dm_clip_hi, d, as_stream(stream), nullptr);
+    if (rc != 1) return rc;
+  }
   PipeArgs a{raw, nullptr, y, nullptr, params, param_stride, H, W, 0, dm_clip_hi, 0};
   return launch_pipeline<MODE_FWD>(a, d, N, dm_kind, false, as_stream(stream));
 }
@@ -389,7 +408,10 @@ extern "C" size_t risp_pipeline_step_workspace(int N, int H, int W, int P) {
   (void)P;
   if (N <= 0 || H <= 0 || W <= 0) return 0;
   PipeGeom g = pipe_geometry(N, H, W);
-  return (size_t)N * g.warps_per_image * RISP_NSLOT * sizeof(float) + finalize_rows_workspace(N, RISP_NSLOT);
+  size_t rows = (size_t)g.warps_per_image;
+  const size_t frows = (size_t)fused_partial_rows_per_frame(N, H, W);
+  if (frows > rows) rows = frows;
+  return (size_t)N * rows * RISP_NSLOT * sizeof(float) + finalize_rows_workspace(N, RISP_NSLOT);
 }
 
 static int pipeline_step_impl(const char* who, bool gt_is_dy, const float* raw, const float* gt, float* y_out,
@@ -417,12 +439,18 @@ static int pipeline_step_impl(const char* who, bool gt_is_dy, const float* raw, 
   cudaStream_t st = as_stream(stream);
   PipeGeom g = pipe_geometry(N, H, W);
   float* partial = static_cast<float*>(workspace);
-  PipeArgs a{raw, gt, y_out, partial, params, param_stride, H, W, 0, dm_clip_hi, gt_is_dy ? 1 : 0};
-  rc = launch_pipeline<MODE_STEP>(a, d, N, dm_kind, big, st);
+  void* fin_ws = reinterpret_cast<char*>(workspace) + (need - finalize_rows_workspace(N, RISP_NSLOT));
+  int frows = 0;
+  rc = (P > 0 && use_fused()) ? fused_launch(gt_is_dy ? 2 : 1, raw, gt, y_out, partial, params, param_stride, N, H, W, dm_kind, dm_clip_hi, d, st, &frows) : 1;
+  if (rc == 1) {
+    PipeArgs a{raw, gt, y_out, partial, params, param_stride, H, W, 0, dm_clip_hi, gt_is_dy ? 1 : 0};
+    rc = launch_pipeline<MODE_STEP>(a, d, N, dm_kind, big, st);
+  } else if (rc == RISP_OK) {
+    g.warps_per_image = frows;
+  }
   if (rc != RISP_OK) return rc;
   const double numel = (double)N * 3.0 * H * W;
   const bool shared_row = (param_stride == 0);
-  void* fin_ws = partial + (size_t)N * g.warps_per_image * RISP_NSLOT;
   if (N > 64 || P == 0) {
     // rare shapes: the one-warp-per-entry finaliser
     if (!gt_is_dy) {
