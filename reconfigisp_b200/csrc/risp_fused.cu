@@ -21,7 +21,7 @@ namespace fused {
 __constant__ float g_cpar[kCSlots][kCRows][kCRowFloats];
 
 enum { MODE_FWD = 0, MODE_STEP = 1, MODE_BWD = 2 };
-constexpr int kWarps = 4;
+constexpr int kWarps = 1;     // one warp per CTA: everything but the lane index is CTA-uniform (uniform datapath, no R2UR)
 constexpr int kStrip = 128;
 
 struct FusedArgs {
@@ -82,69 +82,66 @@ __global__ void fused_prep_kernel(const float* __restrict__ params, int pstride,
   }
 }
 
-// ---- raw rows: issue / finish with the horizontal halo by shuffle ------------------------------------------------------
-// A lane loads its 4 columns with one 128-bit load.  The horizontal halo comes from the neighbouring lanes by shuffle;
-// only the lanes at the two ends of the strip load it from memory, and the reflect-101 border is folded into the ADDRESS of
-// that load (column -1 -> 1, column W -> W-2), so finishing a row needs no border logic at all.
-template <int HL> struct RawRow;
-template <> struct RawRow<1> { float4 v; float l, r; };
-template <> struct RawRow<2> { float4 v; float2 l, r; };
+// ---- per-warp row ring in shared memory, filled by bulk async copies (TMA, 1-D) ----------------------------------------
+// Each warp owns a ring of D row records: [raw strip with a 4-column pad on both sides | GT B | GT G | GT R].  One elected
+// lane issues the copies of a whole row (cp.async.bulk ... mbarrier::complete_tx) D - 2*HL - 1 rows ahead of the row being
+// computed, so 3-5 rows (2 KB each) per warp are in flight without a single register: enough bytes in flight for HBM
+// (Little's law wants ~40 KB per SM) at 8 warps per SM.  Lanes read their window with LDS: 128-bit own columns plus the two
+// halo columns, whose offsets fold the reflect-101 frame border (column -1 -> 1, column W -> W-2) -- no shuffles, no
+// register window, no prefetch registers.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t mbar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n"
+               : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must trap (and fail the launch) instead of hanging the device
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try(mbar, parity); ++spin)
+    if (spin > (1u << 26)) __trap();
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ float4 lds4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds1(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
-struct LaneGeom {       // per item, per lane
-  bool active, endL, endR;   // inside the frame; loads the left / right halo itself
-  int offL, offR;            // element offset of that load relative to the lane's first column
+constexpr int kRingD = 8;          // records per warp
+constexpr int kPad = 4;            // floats of halo pad on each side of the raw strip
+template <int MODE>
+struct RingCfg {
+  static constexpr int RAWF = kStrip + 2 * kPad;                         // floats of the raw part
+  static constexpr int GTF = (MODE == 0 /*MODE_FWD*/) ? 0 : 3 * kStrip;  // floats of the GT part
+  static constexpr int RECB = (RAWF + GTF) * 4;                          // bytes per record (multiple of 16)
+  static constexpr int WARPB = kRingD * RECB;
+  static constexpr int SMEM = kWarps * WARPB + kWarps * kRingD * 8;      // records + mbarriers
 };
 
-template <int HL>
-__device__ __forceinline__ LaneGeom lane_geom(int c0, int W, int lane) {
-  LaneGeom g;
-  g.active = c0 < W;
-  const bool first = (c0 == 0), last = g.active && (c0 + 4 >= W);
-  g.endL = g.active && lane == 0;
-  g.endR = g.active && (lane == 31 || last);
-  if (HL == 1) { g.offL = first ? 1 : -1; g.offR = last ? 2 : 4; }
-  else         { g.offL = first ? 1 : -2; g.offR = last ? 1 : 4; }   // float2 loads: cols (1,2) reversed / (W-3,W-2) reversed
-  return g;
-}
-
 __device__ __forceinline__ int reflect101(int r, int H) { return r < 0 ? -r : (r >= H ? 2 * H - 2 - r : r); }
-
-// issue the loads of one raw row (rp = the lane's first column of that row) -- no dependent instruction here
-template <int HL>
-__device__ __forceinline__ void row_issue(RawRow<HL>& q, const float* __restrict__ rp, const LaneGeom& g) {
-  q.v = g.active ? __ldg(reinterpret_cast<const float4*>(rp)) : make_float4(0.f, 0.f, 0.f, 0.f);
-  if constexpr (HL == 1) {
-    q.l = 0.f; q.r = 0.f;
-    if (g.endL) q.l = __ldg(rp + g.offL);
-    if (g.endR) q.r = __ldg(rp + g.offR);
-  } else {
-    q.l = make_float2(0.f, 0.f); q.r = make_float2(0.f, 0.f);
-    if (g.endL) { q.l.x = __ldg(rp + g.offL); q.l.y = __ldg(rp + g.offL + 1); }
-    if (g.endR) { q.r.x = __ldg(rp + g.offR); q.r.y = __ldg(rp + g.offR + 1); }
-  }
-}
-
-// halo exchange: dst[0 .. 4+2*HL) = columns c0-HL .. c0+3+HL of the row
-template <int HL>
-__device__ __forceinline__ void row_finish(float (&dst)[4 + 2 * HL], const RawRow<HL>& q, int W, int c0, const LaneGeom& g) {
-  const unsigned full = 0xffffffffu;
-  const float4 v = q.v;
-  const bool first = (c0 == 0), last = g.active && (c0 + 4 >= W);
-  if constexpr (HL == 1) {
-    float l = __shfl_up_sync(full, v.w, 1), r = __shfl_down_sync(full, v.x, 1);
-    if (g.endL) l = q.l;
-    if (g.endR) r = q.r;
-    dst[0] = l; dst[1] = v.x; dst[2] = v.y; dst[3] = v.z; dst[4] = v.w; dst[5] = r;
-  } else {
-    float l0 = __shfl_up_sync(full, v.z, 1), l1 = __shfl_up_sync(full, v.w, 1);
-    float r0 = __shfl_down_sync(full, v.x, 1), r1 = __shfl_down_sync(full, v.y, 1);
-    // interior strip ends load (c0-2, c0-1) / (c0+4, c0+5); at the frame border the pair is the reflected one, reversed:
-    // cols (-2,-1) = cols (2,1), loaded as (1,2);  cols (W, W+1) = cols (W-2, W-3), loaded as (W-3, W-2)
-    if (g.endL) { l0 = first ? q.l.y : q.l.x; l1 = first ? q.l.x : q.l.y; }
-    if (g.endR) { r0 = last ? q.r.y : q.r.x; r1 = last ? q.r.x : q.r.y; }
-    dst[0] = l0; dst[1] = l1; dst[2] = v.x; dst[3] = v.y; dst[4] = v.z; dst[5] = v.w; dst[6] = r0; dst[7] = r1;
-  }
-}
 
 // ---- demosaic of the lane's 4 pixels; row parity is a template parameter (no selects) ---------------------------------
 // w[RO + j][i]: raw row r-HL+j, column c0-HL+i.  Sites: (even,even)=R (even,odd)=G1 (odd,even)=G2 (odd,odd)=B.
@@ -349,10 +346,10 @@ __device__ __forceinline__ bool chain_slow(const float* __restrict__ cp) {
 }
 
 #ifndef RISP_FUSED_STEP_MINB
-#define RISP_FUSED_STEP_MINB 2
+#define RISP_FUSED_STEP_MINB 8
 #endif
 #ifndef RISP_FUSED_FWD_MINB
-#define RISP_FUSED_FWD_MINB 4
+#define RISP_FUSED_FWD_MINB 16
 #endif
 
 template <int DM, int MODE, unsigned SIG>
@@ -362,15 +359,19 @@ fused_kernel(FusedArgs a, ChainDesc d) {
   constexpr int HL = (DM == RISP_DM_MALVAR) ? 2 : 1;
   constexpr int WR = 2 * HL + 1, WC = 4 + 2 * HL;
   constexpr int NACC = (MODE == MODE_FWD) ? 1 : E.nacc;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int n = blockIdx.y, j0 = blockIdx.x;       // frame, CTA within the frame (both uniform: constants go to URs)
+  using RC = RingCfg<MODE>;
+  constexpr int D = kRingD;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x;
+  constexpr int wid = 0;
+  const int n = blockIdx.y, j0 = blockIdx.x;       // frame, CTA within the frame (both uniform)
   const int H = a.H, W = a.W;
   const long long plane = (long long)H * W;
   const float* __restrict__ img = a.raw + (long long)n * plane;
   const float* __restrict__ gtb = (MODE != MODE_FWD) ? a.gt + (long long)n * 3 * plane : nullptr;
   float* __restrict__ yb = a.y ? a.y + (long long)n * 3 * plane : nullptr;
-  // derived constants of this frame's parameter row (written by fused_prep_kernel earlier on the stream): loaded once,
-  // they stay in registers for the whole kernel and enter the packed instructions as broadcast scalars (R.F32)
+  // derived constants of this frame's parameter row (written by fused_prep_kernel earlier on the stream): they enter the
+  // packed instructions as broadcast scalars from uniform registers
   float cst[E.ncst];
   {
     const float* __restrict__ crow = &g_cpar[a.slot][a.pstride ? n : 0][0];
@@ -380,6 +381,19 @@ fused_kernel(FusedArgs a, ChainDesc d) {
   const float* cp = cst;
   const bool slow = chain_slow<SIG>(cp);
 
+  // ---- ring set-up: zero the records (out-of-frame columns are never written by a copy and must stay finite), barriers
+  const uint32_t ring = smem_u32(smem_raw) + wid * RC::WARPB;
+  const uint32_t bars = smem_u32(smem_raw) + kWarps * RC::WARPB + wid * D * 8;
+  for (int i = lane; i < RC::WARPB / 16; i += 32) sts4(ring + i * 16, make_float4(0.f, 0.f, 0.f, 0.f));
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < D; ++s) mbar_init(bars + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  unsigned gcount = 0;        // records issued so far by this warp (identical in all warps of the CTA)
+
   float2 acc[NACC];
   float2 loss = zero2();
 #pragma unroll
@@ -388,49 +402,96 @@ fused_kernel(FusedArgs a, ChainDesc d) {
   const int items = a.chunks * a.strip_blocks;
   for (int item = j0; item < items; item += a.cpf) {
     const int chunk = item / a.strip_blocks, sb = item - chunk * a.strip_blocks;
-    const int strip = sb * kWarps + wid;
-    const int c0 = strip * kStrip + lane * 4;
-    const LaneGeom lg = lane_geom<HL>(c0, W, lane);
-    const bool active = lg.active;
+    const int strip = sb;
+    constexpr bool ghost = false;
+    const int c0s = strip * kStrip;                 // first column of the strip
+    const int c0 = c0s + lane * 4;
+    const bool active = !ghost && c0 < W;
+    const bool first = (c0 == 0), last = active && (c0 + 4 >= W);
     const float lane_w = active ? 1.f : 0.f;
     const int ra = chunk * a.rows_per_chunk;
     const int rb = min(H, ra + a.rows_per_chunk);
-    const float* __restrict__ rawl = img + c0;                          // the lane's first column, row 0
-    const float* __restrict__ gtl = (MODE != MODE_FWD) ? gtb + c0 : nullptr;
-    float* __restrict__ yl = yb ? yb + c0 : nullptr;
-
-    float w[WR + 1][WC];
-    RawRow<HL> q;
+    const int nrec = (rb - ra) + 2 * HL;            // record k: raw row ra-HL+k (reflected), GT row ra+k-2HL (k >= 2HL)
+    // copy geometry of the strip: raw columns [cs, ce) land at pad offset (cs - (c0s - kPad)); GT columns [c0s, ge)
+    const int cs = (c0s >= kPad) ? c0s - kPad : 0, ce = min(c0s + kStrip + kPad, W), ge = min(c0s + kStrip, W);
+    const uint32_t raw_dst_off = (uint32_t)(cs - (c0s - kPad)) * 4u;
+    const uint32_t raw_bytes = ghost ? 0u : (uint32_t)(ce - cs) * 4u, gt_bytes = ghost ? 0u : (uint32_t)(ge - c0s) * 4u;
+    // lanes outside the frame read zeros: nothing is copied over their columns during this item
+    if (!active) {
 #pragma unroll
-    for (int j = 0; j < WR - 1; ++j) {
-      row_issue<HL>(q, rawl + (size_t)reflect101(ra - HL + j, H) * W, lg);
-      row_finish<HL>(w[j], q, W, c0, lg);
+      for (int s = 0; s < D; ++s) {
+        sts4(ring + s * RC::RECB + (kPad + lane * 4) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+        if (MODE != MODE_FWD) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) sts4(ring + s * RC::RECB + (RC::RAWF + c * kStrip + lane * 4) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+      }
     }
-    row_issue<HL>(q, rawl + (size_t)reflect101(ra + HL, H) * W, lg);
-    // GT rows ping-pong between two register sets (even rows in g0, odd rows in g1): the next row's loads never overwrite
-    // the row being consumed, so no copies
-    float4 g0[3], g1[3];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+
+    auto issue = [&](int k) {        // one elected lane: the copies of record k of this item
+      const unsigned g = gcount + (unsigned)k;
+      const uint32_t slot = g & (D - 1);
+      const uint32_t rec = ring + slot * RC::RECB, bar = bars + slot * 8;
+      const bool has_gt = (MODE != MODE_FWD) && (k >= 2 * HL);
+      mbar_expect_tx(bar, raw_bytes + (has_gt ? 3u * gt_bytes : 0u));
+      if (!ghost) {
+        const int rr = reflect101(ra - HL + k, H);
+        bulk_g2s(rec + raw_dst_off, img + (size_t)rr * W + cs, raw_bytes, bar);
+        if (has_gt) {
+          const float* gp = gtb + (size_t)(ra + k - 2 * HL) * W + c0s;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { g0[c] = make_float4(0.f, 0.f, 0.f, 0.f); g1[c] = g0[c]; }
-    auto gt_issue = [&](float4 (&g)[3], int row) {
-      if (MODE != MODE_FWD && active) {
-        const float* pr = gtl + (size_t)row * W;
-        g[0] = ld_stream4(pr); g[1] = ld_stream4(pr + plane); g[2] = ld_stream4(pr + 2 * plane);
+          for (int c = 0; c < 3; ++c) bulk_g2s(rec + (RC::RAWF + c * kStrip) * 4, gp + c * plane, gt_bytes, bar);
+        }
       }
     };
-    gt_issue(g0, ra);
+    auto wait_rec = [&](int k) {
+      const unsigned g = gcount + (unsigned)k;
+      mbar_wait(bars + (g & (D - 1)) * 8, (g / D) & 1u);
+    };
+    if (elect_one()) {
+      for (int k = 0; k < D && k < nrec; ++k) issue(k);
+    }
+    __syncwarp();
+    for (int k = 0; k < 2 * HL; ++k) wait_rec(k);
 
-    // one row: finish the in-flight raw row into the window, prefetch the next raw / GT row, demosaic, chain, store
-    auto do_row = [&](auto ro_tag, auto odd_tag, int r, bool more, const float4 (&tg)[3], float4 (&gnext)[3]) {
-      constexpr int RO = decltype(ro_tag)::value;
+    // lane offsets inside a record (bytes): own 4 columns, left / right halo with the frame border folded in
+    const uint32_t own = (uint32_t)(kPad + lane * 4) * 4u;
+    const int oL0 = first ? (HL == 1 ? 1 : 2) : -HL;           // column c0-HL   (reflect: -1 -> 1, -2 -> 2)
+    const int oL1 = first ? 1 : -1;                            // column c0-1    (HL == 2 only)
+    const int oR0 = last ? 2 : 4;                              // column c0+4    (reflect: W -> W-2)
+    const int oR1 = last ? 1 : 5;                              // column c0+5    (reflect: W+1 -> W-3)
+
+    // one row: wait for its newest raw row / GT row, read the window, refill the oldest slot, demosaic, chain, store
+    auto do_row = [&](auto odd_tag, int i) {
       constexpr bool ODD = decltype(odd_tag)::value;
-      row_finish<HL>(w[RO + WR - 1], q, W, c0, lg);
-      if (more) {
-        row_issue<HL>(q, rawl + (size_t)reflect101(r + 1 + HL, H) * W, lg);
-        gt_issue(gnext, r + 1);
+      wait_rec(i + 2 * HL);
+      float w[WR][WC];
+#pragma unroll
+      for (int j = 0; j < WR; ++j) {
+        const uint32_t rec = ring + ((gcount + (unsigned)(i + j)) & (D - 1)) * RC::RECB + own;
+        const float4 v = lds4(rec);
+        if constexpr (HL == 1) {
+          w[j][0] = lds1(rec + oL0 * 4); w[j][1] = v.x; w[j][2] = v.y; w[j][3] = v.z; w[j][4] = v.w; w[j][5] = lds1(rec + oR0 * 4);
+        } else {
+          w[j][0] = lds1(rec + oL0 * 4); w[j][1] = lds1(rec + oL1 * 4);
+          w[j][2] = v.x; w[j][3] = v.y; w[j][4] = v.z; w[j][5] = v.w;
+          w[j][6] = lds1(rec + oR0 * 4); w[j][7] = lds1(rec + oR1 * 4);
+        }
+      }
+      float4 tg[3];
+      if constexpr (MODE != MODE_FWD) {
+        const uint32_t rec = ring + ((gcount + (unsigned)(i + 2 * HL)) & (D - 1)) * RC::RECB + (RC::RAWF + lane * 4) * 4;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tg[c] = lds4(rec + c * kStrip * 4);
+      }
+      __syncwarp();                                    // every lane has read record i: its slot may be refilled
+      if (i + D < nrec) {
+        if (elect_one()) issue(i + D);
       }
       P2 lo, hi;
-      demosaic4<DM, HL, RO, ODD, WR + 1>(w, a.clip_hi, lo, hi);
+      demosaic4<DM, HL, 0, ODD, WR>(w, a.clip_hi, lo, hi);
       P2 ylo, yhi;
       if constexpr (MODE == MODE_FWD) {
         ylo = Fwd<SIG, 0>::go(lo, cp, slow);
@@ -443,21 +504,19 @@ fused_kernel(FusedArgs a, ChainDesc d) {
         Run<SIG, 0, MODE>::go(hi, thi, cp, acc, loss, yhi, slow, lane_w);
       }
       if ((MODE == MODE_FWD || yb) && active) {
-        float* po = yl + (size_t)r * W;
+        float* po = yb + (size_t)(ra + i) * W + c0;
         st_stream4(po, make_float4(ylo.b.x, ylo.b.y, yhi.b.x, yhi.b.y));
         st_stream4(po + plane, make_float4(ylo.g.x, ylo.g.y, yhi.g.x, yhi.g.y));
         st_stream4(po + 2 * plane, make_float4(ylo.r.x, ylo.r.y, yhi.r.x, yhi.r.y));
       }
     };
 
-    for (int r = ra; r < rb; r += 2) {      // ra, rb even
-      do_row(std::integral_constant<int, 0>{}, std::false_type{}, r, true, g0, g1);
-      do_row(std::integral_constant<int, 1>{}, std::true_type{}, r + 1, r + 2 < rb, g1, g0);
-#pragma unroll
-      for (int j = 0; j < WR - 1; ++j)
-#pragma unroll
-        for (int i = 0; i < WC; ++i) w[j][i] = w[j + 2][i];
+    const int nrows = rb - ra;               // even
+    for (int i = 0; i < nrows; i += 2) {
+      do_row(std::false_type{}, i);
+      do_row(std::true_type{}, i + 1);
     }
+    gcount += (unsigned)nrec;
   }
 
   if constexpr (MODE != MODE_FWD) {
@@ -467,7 +526,7 @@ fused_kernel(FusedArgs a, ChainDesc d) {
     for (int i = 0; i < NACC; ++i) tot[i] = warp_sum(acc[i].x + acc[i].y);
     const float lsum = warp_sum(loss.x + loss.y);
     if (lane == 0) {
-      float* __restrict__ out = a.partial + (((long long)n * a.cpf + j0) * kWarps + wid) * RISP_NSLOT;
+      float* __restrict__ out = a.partial + ((long long)n * a.cpf + j0) * RISP_NSLOT;
 #pragma unroll
       for (int i = 0; i < RISP_NSLOT; ++i) out[i] = 0.f;
       out[RISP_SLOT_LOSS] = lsum;
@@ -570,7 +629,8 @@ template <int DM, int MODE, unsigned SIG>
 static int resident_ctas() {
   static int n = 0;
   if (n == 0) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused_kernel<DM, MODE, SIG>, kWarps * 32, 0) != cudaSuccess || n < 1) n = 1;
+    cudaFuncSetAttribute(fused_kernel<DM, MODE, SIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, RingCfg<MODE>::SMEM);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused_kernel<DM, MODE, SIG>, kWarps * 32, RingCfg<MODE>::SMEM) != cudaSuccess || n < 1) n = 1;
   }
   return n;
 }
@@ -580,7 +640,7 @@ static int launch_one(FusedArgs a, const ChainDesc& d, int N, cudaStream_t st, G
   const Geometry g = geometry(N, a.H, a.W, resident_ctas<DM, MODE, SIG>());
   if (gout) { *gout = g; return RISP_OK; }
   a.rows_per_chunk = g.rows_per_chunk; a.chunks = g.chunks; a.strip_blocks = g.strip_blocks; a.cpf = g.cpf;
-  fused_kernel<DM, MODE, SIG><<<dim3(g.cpf, N), kWarps * 32, 0, st>>>(a, d);
+  fused_kernel<DM, MODE, SIG><<<dim3(g.cpf, N), kWarps * 32, RingCfg<MODE>::SMEM, st>>>(a, d);
   return check_launch("fused_kernel");
 }
 
@@ -612,8 +672,8 @@ bool fused_handles(const ChainDesc& d, int N, int param_stride, int H, int W) {
 
 // partial rows the step / backward kernels write: [N][rows_per_frame][RISP_NSLOT]
 int fused_partial_rows_per_frame(int N, int H, int W) {
-  // the largest grid any instantiation may use: 8 resident CTAs per SM is an upper bound for 128-thread CTAs here
-  int slots = sm_count() * 8;
+  // the largest grid any instantiation may use: 32 resident CTAs per SM is the hardware bound
+  int slots = sm_count() * 32;
   int cpf = slots / N < 1 ? 1 : slots / N;
   (void)H; (void)W;
   return cpf * fused::kWarps;
