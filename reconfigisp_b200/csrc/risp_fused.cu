@@ -13,6 +13,7 @@
 //   * the chain runs on pixel PAIRS with FFMA2/FMUL2/FADD2, coefficients from uniform registers (risp_fused.cuh).
 #include "risp_fused.cuh"
 
+#include <cuda.h>
 #include <mutex>
 
 namespace risp {
@@ -130,15 +131,22 @@ __device__ __forceinline__ void sts4(uint32_t addr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-constexpr int kRingD = 8;          // records per warp
+// tensor-map TMA: one instruction moves a (columns x rows x planes) box; out-of-bounds elements arrive as zeros
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int x, int y, int z, uint32_t mbar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(mbar) : "memory");
+}
+
 constexpr int kPad = 4;            // floats of halo pad on each side of the raw strip
 template <int MODE>
 struct RingCfg {
-  static constexpr int RAWF = kStrip + 2 * kPad;                         // floats of the raw part
-  static constexpr int GTF = (MODE == 0 /*MODE_FWD*/) ? 0 : 3 * kStrip;  // floats of the GT part
-  static constexpr int RECB = (RAWF + GTF) * 4;                          // bytes per record (multiple of 16)
-  static constexpr int WARPB = kRingD * RECB;
-  static constexpr int SMEM = kWarps * WARPB + kWarps * kRingD * 8;      // records + mbarriers
+  static constexpr int D = (MODE == 0 /*MODE_FWD*/) ? 8 : 4;             // records per warp, two rows each
+  static constexpr int RAWROWB = (kStrip + 2 * kPad) * 4;                // 544 B: one raw row of the box
+  static constexpr int RAWB = 1152;                                      // two rows (1088 B), padded to a 128-B multiple
+  static constexpr int GTB = (MODE == 0 /*MODE_FWD*/) ? 0 : 3 * 2 * kStrip * 4;   // [plane][row][128]
+  static constexpr int RECB = RAWB + GTB;                                // multiple of 128
+  static constexpr int WARPB = D * RECB;
+  static constexpr int SMEM = kWarps * WARPB + kWarps * D * 8 + 128;  // records + mbarriers + alignment slack
 };
 
 __device__ __forceinline__ int reflect101(int r, int H) { return r < 0 ? -r : (r >= H ? 2 * H - 2 - r : r); }
@@ -354,21 +362,18 @@ __device__ __forceinline__ bool chain_slow(const float* __restrict__ cp) {
 
 template <int DM, int MODE, unsigned SIG>
 __global__ void __launch_bounds__(kWarps * 32, (MODE == MODE_FWD) ? RISP_FUSED_FWD_MINB : RISP_FUSED_STEP_MINB)
-fused_kernel(FusedArgs a, ChainDesc d) {
+fused_kernel(FusedArgs a, ChainDesc d, const __grid_constant__ CUtensorMap tm_raw, const __grid_constant__ CUtensorMap tm_gt) {
   constexpr EffChain E = Eff<SIG>::e;
   constexpr int HL = (DM == RISP_DM_MALVAR) ? 2 : 1;
   constexpr int WR = 2 * HL + 1, WC = 4 + 2 * HL;
   constexpr int NACC = (MODE == MODE_FWD) ? 1 : E.nacc;
   using RC = RingCfg<MODE>;
-  constexpr int D = kRingD;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int D = RC::D;
+  extern __shared__ unsigned char smem_raw[];
   const int lane = threadIdx.x;
-  constexpr int wid = 0;
   const int n = blockIdx.y, j0 = blockIdx.x;       // frame, CTA within the frame (both uniform)
   const int H = a.H, W = a.W;
   const long long plane = (long long)H * W;
-  const float* __restrict__ img = a.raw + (long long)n * plane;
-  const float* __restrict__ gtb = (MODE != MODE_FWD) ? a.gt + (long long)n * 3 * plane : nullptr;
   float* __restrict__ yb = a.y ? a.y + (long long)n * 3 * plane : nullptr;
   // derived constants of this frame's parameter row (written by fused_prep_kernel earlier on the stream): they enter the
   // packed instructions as broadcast scalars from uniform registers
@@ -381,18 +386,16 @@ fused_kernel(FusedArgs a, ChainDesc d) {
   const float* cp = cst;
   const bool slow = chain_slow<SIG>(cp);
 
-  // ---- ring set-up: zero the records (out-of-frame columns are never written by a copy and must stay finite), barriers
-  const uint32_t ring = smem_u32(smem_raw) + wid * RC::WARPB;
-  const uint32_t bars = smem_u32(smem_raw) + kWarps * RC::WARPB + wid * D * 8;
-  for (int i = lane; i < RC::WARPB / 16; i += 32) sts4(ring + i * 16, make_float4(0.f, 0.f, 0.f, 0.f));
+  // ---- ring set-up -------------------------------------------------------------------------------------------------
+  const uint32_t ring = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t bars = ring + RC::WARPB;
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < D; ++s) mbar_init(bars + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncwarp();
-  unsigned gcount = 0;        // records issued so far by this warp (identical in all warps of the CTA)
+  unsigned gcount = 0;        // records issued before the current item
 
   float2 acc[NACC];
   float2 loss = zero2();
@@ -401,94 +404,63 @@ fused_kernel(FusedArgs a, ChainDesc d) {
 
   const int items = a.chunks * a.strip_blocks;
   for (int item = j0; item < items; item += a.cpf) {
-    const int chunk = item / a.strip_blocks, sb = item - chunk * a.strip_blocks;
-    const int strip = sb;
-    constexpr bool ghost = false;
+    const int chunk = item / a.strip_blocks, strip = item - chunk * a.strip_blocks;
     const int c0s = strip * kStrip;                 // first column of the strip
     const int c0 = c0s + lane * 4;
-    const bool active = !ghost && c0 < W;
+    const bool active = c0 < W;                     // columns beyond the frame arrive as zeros (TMA out-of-bounds fill)
     const bool first = (c0 == 0), last = active && (c0 + 4 >= W);
     const float lane_w = active ? 1.f : 0.f;
     const int ra = chunk * a.rows_per_chunk;
     const int rb = min(H, ra + a.rows_per_chunk);
-    const int nrec = (rb - ra) + 2 * HL;            // record k: raw row ra-HL+k (reflected), GT row ra+k-2HL (k >= 2HL)
-    // copy geometry of the strip: raw columns [cs, ce) land at pad offset (cs - (c0s - kPad)); GT columns [c0s, ge)
-    const int cs = (c0s >= kPad) ? c0s - kPad : 0, ce = min(c0s + kStrip + kPad, W), ge = min(c0s + kStrip, W);
-    const uint32_t raw_dst_off = (uint32_t)(cs - (c0s - kPad)) * 4u;
-    const uint32_t raw_bytes = ghost ? 0u : (uint32_t)(ce - cs) * 4u, gt_bytes = ghost ? 0u : (uint32_t)(ge - c0s) * 4u;
-    // lanes outside the frame read zeros: nothing is copied over their columns during this item
-    if (!active) {
-#pragma unroll
-      for (int s = 0; s < D; ++s) {
-        sts4(ring + s * RC::RECB + (kPad + lane * 4) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
-        if (MODE != MODE_FWD) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) sts4(ring + s * RC::RECB + (RC::RAWF + c * kStrip + lane * 4) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
-        }
-      }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
+    const int rbase = ra - 2;                       // record k of the item holds physical rows rbase+2k, rbase+2k+1
+    const int nrec = (rb - ra) / 2 + 2;
 
-    auto issue = [&](int k) {        // one elected lane: the copies of record k of this item
+    auto issue = [&](int k) {        // one elected lane: the two TMA boxes of record k
       const unsigned g = gcount + (unsigned)k;
-      const uint32_t slot = g & (D - 1);
-      const uint32_t rec = ring + slot * RC::RECB, bar = bars + slot * 8;
-      const bool has_gt = (MODE != MODE_FWD) && (k >= 2 * HL);
-      mbar_expect_tx(bar, raw_bytes + (has_gt ? 3u * gt_bytes : 0u));
-      if (!ghost) {
-        const int rr = reflect101(ra - HL + k, H);
-        bulk_g2s(rec + raw_dst_off, img + (size_t)rr * W + cs, raw_bytes, bar);
-        if (has_gt) {
-          const float* gp = gtb + (size_t)(ra + k - 2 * HL) * W + c0s;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) bulk_g2s(rec + (RC::RAWF + c * kStrip) * 4, gp + c * plane, gt_bytes, bar);
-        }
-      }
+      const uint32_t rec = ring + (g & (D - 1)) * RC::RECB, bar = bars + (g & (D - 1)) * 8;
+      const bool has_gt = (MODE != MODE_FWD) && (k >= 1) && (k < nrec - 1);
+      mbar_expect_tx(bar, 2u * RC::RAWROWB + (has_gt ? (uint32_t)RC::GTB : 0u));
+      tma_load_3d(rec, &tm_raw, c0s - kPad, rbase + 2 * k, n, bar);
+      if (has_gt) tma_load_3d(rec + RC::RAWB, &tm_gt, c0s, rbase + 2 * k, 3 * n, bar);
     };
     auto wait_rec = [&](int k) {
       const unsigned g = gcount + (unsigned)k;
       mbar_wait(bars + (g & (D - 1)) * 8, (g / D) & 1u);
     };
+    // shared-memory address of physical raw row q (reflect-101 at the frame border) -- uniform
+    auto row_addr = [&](int q) -> uint32_t {
+      const int qq = reflect101(q, H);
+      const unsigned g = gcount + (unsigned)((qq - rbase) >> 1);
+      return ring + (g & (D - 1)) * RC::RECB + (uint32_t)(qq & 1) * RC::RAWROWB;
+    };
     if (elect_one()) {
       for (int k = 0; k < D && k < nrec; ++k) issue(k);
     }
     __syncwarp();
-    for (int k = 0; k < 2 * HL; ++k) wait_rec(k);
+    wait_rec(0);
+    wait_rec(1);
 
-    // lane offsets inside a record (bytes): own 4 columns, left / right halo with the frame border folded in
+    // lane offsets inside a raw row (bytes): own 4 columns, left / right halo with the frame border folded in
     const uint32_t own = (uint32_t)(kPad + lane * 4) * 4u;
-    const int oL0 = first ? (HL == 1 ? 1 : 2) : -HL;           // column c0-HL   (reflect: -1 -> 1, -2 -> 2)
-    const int oL1 = first ? 1 : -1;                            // column c0-1    (HL == 2 only)
-    const int oR0 = last ? 2 : 4;                              // column c0+4    (reflect: W -> W-2)
-    const int oR1 = last ? 1 : 5;                              // column c0+5    (reflect: W+1 -> W-3)
+    const uint32_t oL0 = own + (first ? (HL == 1 ? 4 : 8) : -4 * HL);    // column c0-HL   (reflect: -1 -> 1, -2 -> 2)
+    const uint32_t oL1 = own + (first ? 4 : -4);                         // column c0-1    (HL == 2 only)
+    const uint32_t oR0 = own + (last ? 8 : 16);                          // column c0+4    (reflect: W -> W-2)
+    const uint32_t oR1 = own + (last ? 4 : 20);                          // column c0+5    (reflect: W+1 -> W-3)
 
-    // one row: wait for its newest raw row / GT row, read the window, refill the oldest slot, demosaic, chain, store
-    auto do_row = [&](auto odd_tag, int i) {
+    // one row: read the window and the GT row, demosaic, chain, store
+    auto do_row = [&](auto odd_tag, int r, const uint32_t* wa, uint32_t gta) {
       constexpr bool ODD = decltype(odd_tag)::value;
-      wait_rec(i + 2 * HL);
       float w[WR][WC];
 #pragma unroll
       for (int j = 0; j < WR; ++j) {
-        const uint32_t rec = ring + ((gcount + (unsigned)(i + j)) & (D - 1)) * RC::RECB + own;
-        const float4 v = lds4(rec);
+        const float4 v = lds4(wa[j] + own);
         if constexpr (HL == 1) {
-          w[j][0] = lds1(rec + oL0 * 4); w[j][1] = v.x; w[j][2] = v.y; w[j][3] = v.z; w[j][4] = v.w; w[j][5] = lds1(rec + oR0 * 4);
+          w[j][0] = lds1(wa[j] + oL0); w[j][1] = v.x; w[j][2] = v.y; w[j][3] = v.z; w[j][4] = v.w; w[j][5] = lds1(wa[j] + oR0);
         } else {
-          w[j][0] = lds1(rec + oL0 * 4); w[j][1] = lds1(rec + oL1 * 4);
+          w[j][0] = lds1(wa[j] + oL0); w[j][1] = lds1(wa[j] + oL1);
           w[j][2] = v.x; w[j][3] = v.y; w[j][4] = v.z; w[j][5] = v.w;
-          w[j][6] = lds1(rec + oR0 * 4); w[j][7] = lds1(rec + oR1 * 4);
+          w[j][6] = lds1(wa[j] + oR0); w[j][7] = lds1(wa[j] + oR1);
         }
-      }
-      float4 tg[3];
-      if constexpr (MODE != MODE_FWD) {
-        const uint32_t rec = ring + ((gcount + (unsigned)(i + 2 * HL)) & (D - 1)) * RC::RECB + (RC::RAWF + lane * 4) * 4;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) tg[c] = lds4(rec + c * kStrip * 4);
-      }
-      __syncwarp();                                    // every lane has read record i: its slot may be refilled
-      if (i + D < nrec) {
-        if (elect_one()) issue(i + D);
       }
       P2 lo, hi;
       demosaic4<DM, HL, 0, ODD, WR>(w, a.clip_hi, lo, hi);
@@ -497,6 +469,9 @@ fused_kernel(FusedArgs a, ChainDesc d) {
         ylo = Fwd<SIG, 0>::go(lo, cp, slow);
         yhi = Fwd<SIG, 0>::go(hi, cp, slow);
       } else {
+        float4 tg[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tg[c] = lds4(gta + c * 2 * kStrip * 4 + lane * 16);
         P2 tlo, thi;
         tlo.b = make_float2(tg[0].x, tg[0].y); tlo.g = make_float2(tg[1].x, tg[1].y); tlo.r = make_float2(tg[2].x, tg[2].y);
         thi.b = make_float2(tg[0].z, tg[0].w); thi.g = make_float2(tg[1].z, tg[1].w); thi.r = make_float2(tg[2].z, tg[2].w);
@@ -504,17 +479,39 @@ fused_kernel(FusedArgs a, ChainDesc d) {
         Run<SIG, 0, MODE>::go(hi, thi, cp, acc, loss, yhi, slow, lane_w);
       }
       if ((MODE == MODE_FWD || yb) && active) {
-        float* po = yb + (size_t)(ra + i) * W + c0;
+        float* po = yb + (size_t)r * W + c0;
         st_stream4(po, make_float4(ylo.b.x, ylo.b.y, yhi.b.x, yhi.b.y));
         st_stream4(po + plane, make_float4(ylo.g.x, ylo.g.y, yhi.g.x, yhi.g.y));
         st_stream4(po + 2 * plane, make_float4(ylo.r.x, ylo.r.y, yhi.r.x, yhi.r.y));
       }
     };
 
-    const int nrows = rb - ra;               // even
-    for (int i = 0; i < nrows; i += 2) {
-      do_row(std::false_type{}, i);
-      do_row(std::true_type{}, i + 1);
+    // iteration m computes rows r = ra + 2(m-1) (even) and r+1 (odd) from records m-1, m, m+1
+    for (int m = 1; m < nrec - 1; ++m) {
+      const int r = ra + 2 * (m - 1);
+      wait_rec(m + 1);
+      const unsigned gB = gcount + (unsigned)m;
+      const uint32_t recA = ring + ((gB - 1) & (D - 1)) * RC::RECB, recB = ring + (gB & (D - 1)) * RC::RECB,
+                     recC = ring + ((gB + 1) & (D - 1)) * RC::RECB;
+      uint32_t we[WR], wo[WR];
+      if (r >= HL && r + 1 + HL < H) {           // interior: static places
+        if constexpr (HL == 1) {
+          we[0] = recA + RC::RAWROWB; we[1] = recB; we[2] = recB + RC::RAWROWB;
+          wo[0] = recB; wo[1] = recB + RC::RAWROWB; wo[2] = recC;
+        } else {
+          we[0] = recA; we[1] = recA + RC::RAWROWB; we[2] = recB; we[3] = recB + RC::RAWROWB; we[4] = recC;
+          wo[0] = recA + RC::RAWROWB; wo[1] = recB; wo[2] = recB + RC::RAWROWB; wo[3] = recC; wo[4] = recC + RC::RAWROWB;
+        }
+      } else {                                   // first / last rows of the frame: reflected rows
+#pragma unroll
+        for (int j = 0; j < WR; ++j) { we[j] = row_addr(r - HL + j); wo[j] = row_addr(r + 1 - HL + j); }
+      }
+      do_row(std::false_type{}, r, we, recB + RC::RAWB);
+      do_row(std::true_type{}, r + 1, wo, recB + RC::RAWB + kStrip * 4);
+      __syncwarp();                              // every lane has read record m-1: its slot may be refilled
+      if (m - 1 + D < nrec) {
+        if (elect_one()) issue(m - 1 + D);
+      }
     }
     gcount += (unsigned)nrec;
   }
@@ -580,7 +577,7 @@ struct Geometry { int rows_per_chunk, chunks, strip_blocks, cpf, grid; };
 
 static Geometry geometry(int N, int H, int W, int ctas_per_sm) {
   Geometry g;
-  g.strip_blocks = (int)cdiv(W, kStrip * kWarps);
+  g.strip_blocks = (int)cdiv(W, kStrip);     // items are (row chunk, strip): one warp per CTA
   const int slots = sm_count() * ctas_per_sm;
   g.cpf = slots / N < 1 ? 1 : slots / N;
   // rows per chunk: minimise rounds * (rows + per-item overhead); an item costs ~3 extra rows (window fill, exposed latency)
@@ -635,12 +632,51 @@ static int resident_ctas() {
   return n;
 }
 
+// ---- tensor maps (driver entry point resolved through the runtime: no -lcuda) ------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// fp32 tensor (W, H, Z) with rows of W floats, box (bx, 2, bz); out-of-bounds elements read as zero
+static int make_map(CUtensorMap* tm, const float* base, int W, int H, long long Z, int bx, int bz) {
+  EncodeTiledFn fn = encode_fn();
+  RISP_REQUIRE(fn, RISP_E_CUDA, "fused pipeline: cuTensorMapEncodeTiled is not available");
+  const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Z};
+  const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)bx, 2u, (cuuint32_t)bz};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RISP_REQUIRE(r == CUDA_SUCCESS, RISP_E_CUDA, "fused pipeline: cuTensorMapEncodeTiled failed (%d) for %dx%dx%lld", (int)r, W, H, Z);
+  return RISP_OK;
+}
+
 template <int DM, int MODE, unsigned SIG>
 static int launch_one(FusedArgs a, const ChainDesc& d, int N, cudaStream_t st, Geometry* gout) {
   const Geometry g = geometry(N, a.H, a.W, resident_ctas<DM, MODE, SIG>());
   if (gout) { *gout = g; return RISP_OK; }
   a.rows_per_chunk = g.rows_per_chunk; a.chunks = g.chunks; a.strip_blocks = g.strip_blocks; a.cpf = g.cpf;
-  fused_kernel<DM, MODE, SIG><<<dim3(g.cpf, N), kWarps * 32, RingCfg<MODE>::SMEM, st>>>(a, d);
+  CUtensorMap tm_raw, tm_gt;
+  int rc = make_map(&tm_raw, a.raw, a.W, a.H, N, kStrip + 2 * kPad, 1);
+  if (rc != RISP_OK) return rc;
+  if (MODE != MODE_FWD) {
+    rc = make_map(&tm_gt, a.gt, a.W, a.H, 3ll * N, kStrip, 3);
+    if (rc != RISP_OK) return rc;
+  } else {
+    tm_gt = tm_raw;
+  }
+  fused_kernel<DM, MODE, SIG><<<dim3(g.cpf, N), kWarps * 32, RingCfg<MODE>::SMEM, st>>>(a, d, tm_raw, tm_gt);
   return check_launch("fused_kernel");
 }
 
