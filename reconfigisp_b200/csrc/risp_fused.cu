@@ -15,6 +15,7 @@
 
 #include <cuda.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace risp {
 namespace fused {
@@ -36,6 +37,7 @@ struct FusedArgs {
   int rows_per_chunk, chunks, strip_blocks, cpf;   // cpf = CTAs per frame
   float clip_hi;
   int slot;
+  int dbg;              // RISP_FUSED_DEBUG builds: 1 = no stores, 2 = no loads (bandwidth experiments)
 };
 
 // ---- preparation: derived constants of every parameter row ---------------------------------------------------------
@@ -131,6 +133,15 @@ __device__ __forceinline__ void sts4(uint32_t addr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+#ifndef RISP_FUSED_FWD_D
+#define RISP_FUSED_FWD_D 4
+#endif
+#ifndef RISP_FUSED_FWD_RR
+#define RISP_FUSED_FWD_RR 4
+#endif
+#ifndef RISP_FUSED_STEP_D
+#define RISP_FUSED_STEP_D 4
+#endif
 // tensor-map TMA: one instruction moves a (columns x rows x planes) box; out-of-bounds elements arrive as zeros
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int x, int y, int z, uint32_t mbar) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
@@ -140,10 +151,15 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
 constexpr int kPad = 4;            // floats of halo pad on each side of the raw strip
 template <int MODE>
 struct RingCfg {
-  static constexpr int D = (MODE == 0 /*MODE_FWD*/) ? 8 : 4;             // records per warp, two rows each
+  static constexpr int D = (MODE == 0 /*MODE_FWD*/) ? RISP_FUSED_FWD_D : RISP_FUSED_STEP_D;   // records per warp (power of 2)
+  // rows per record = rows per TMA box.  A TMA instruction costs the SM's copy engine ~150 cycles whatever its size
+  // (measured: 1 KB boxes deliver 1.9 TB/s chip-wide), so the inference kernel, which has nothing but the copies to wait
+  // for, uses 4-row boxes; the backward-carrying kernels are issue-bound and keep the smaller ring
+  static constexpr int RR = (MODE == 0 /*MODE_FWD*/) ? RISP_FUSED_FWD_RR : 2;
   static constexpr int RAWROWB = (kStrip + 2 * kPad) * 4;                // 544 B: one raw row of the box
-  static constexpr int RAWB = 1152;                                      // two rows (1088 B), padded to a 128-B multiple
-  static constexpr int GTB = (MODE == 0 /*MODE_FWD*/) ? 0 : 3 * 2 * kStrip * 4;   // [plane][row][128]
+  static constexpr int RAWB = (RR * RAWROWB + 127) / 128 * 128;          // RR rows, padded to a 128-B multiple
+  static constexpr int GTPLANEB = RR * kStrip * 4;
+  static constexpr int GTB = (MODE == 0 /*MODE_FWD*/) ? 0 : 3 * GTPLANEB;  // [plane][row][128]
   static constexpr int RECB = RAWB + GTB;                                // multiple of 128
   static constexpr int WARPB = D * RECB;
   static constexpr int SMEM = kWarps * WARPB + kWarps * D * 8 + 128;  // records + mbarriers + alignment slack
@@ -232,7 +248,9 @@ struct Tail {
       constexpr bool NEED_DX = (K > 0);
       const float* c = cp + E.coff[K];
       float2* a = acc + E.aoff[K];
-      if constexpr (OP == RISP_OP_GAMMA) {
+      if constexpr (OP == RISP_OP_SKIP) {
+        return Tail<SIG, K + 1, MODE, C>::go(x, tgt, cp, acc, loss, yout, slow, lane_w);
+      } else if constexpr (OP == RISP_OP_GAMMA) {
         float2 l2;
         const float gm = c[0];
         const float2 y = gamma_fwd2<IN01>(x, gm, l2);
@@ -334,7 +352,8 @@ struct Fwd {
       constexpr bool IN01 = (K > 0) && fop_out01(E.op[K > 0 ? K - 1 : 0]);
       const float* c = cp + E.coff[K];
       P2 y;
-      if constexpr (OP == RISP_OP_GAMMA) { GammaSaved sv; y = gamma_fwd<IN01>(x, c[0], sv); }
+      if constexpr (OP == RISP_OP_SKIP) { y = x; }
+      else if constexpr (OP == RISP_OP_GAMMA) { GammaSaved sv; y = gamma_fwd<IN01>(x, c[0], sv); }
       else if constexpr (OP == RISP_OP_GAIN) { GainSaved sv; y = gain_fwd(x, c, sv); }
       else if constexpr (OP == RISP_OP_POLY10 || OP == FOP_POLYG) { PolySaved sv; y = poly_fwd(x, c, sv); }
       else { GtmSaved sv; y = gtm_fwd(x, c, sv, slow); }
@@ -366,7 +385,8 @@ fused_kernel(FusedArgs a, ChainDesc d, const __grid_constant__ CUtensorMap tm_ra
   constexpr EffChain E = Eff<SIG>::e;
   constexpr int HL = (DM == RISP_DM_MALVAR) ? 2 : 1;
   constexpr int WR = 2 * HL + 1, WC = 4 + 2 * HL;
-  constexpr int NACC = (MODE == MODE_FWD) ? 1 : E.nacc;
+  constexpr int NACC = (MODE == MODE_FWD || E.nacc == 0) ? 1 : E.nacc;
+  constexpr int NCST = E.ncst > 0 ? E.ncst : 1;
   using RC = RingCfg<MODE>;
   constexpr int D = RC::D;
   extern __shared__ unsigned char smem_raw[];
@@ -377,11 +397,11 @@ fused_kernel(FusedArgs a, ChainDesc d, const __grid_constant__ CUtensorMap tm_ra
   float* __restrict__ yb = a.y ? a.y + (long long)n * 3 * plane : nullptr;
   // derived constants of this frame's parameter row (written by fused_prep_kernel earlier on the stream): they enter the
   // packed instructions as broadcast scalars from uniform registers
-  float cst[E.ncst];
+  float cst[NCST];
   {
     const float* __restrict__ crow = &g_cpar[a.slot][a.pstride ? n : 0][0];
 #pragma unroll
-    for (int i = 0; i < E.ncst; ++i) cst[i] = crow[i];
+    for (int i = 0; i < NCST; ++i) cst[i] = crow[i];
   }
   const float* cp = cst;
   const bool slow = chain_slow<SIG>(cp);
@@ -412,26 +432,34 @@ fused_kernel(FusedArgs a, ChainDesc d, const __grid_constant__ CUtensorMap tm_ra
     const float lane_w = active ? 1.f : 0.f;
     const int ra = chunk * a.rows_per_chunk;
     const int rb = min(H, ra + a.rows_per_chunk);
-    const int rbase = ra - 2;                       // record k of the item holds physical rows rbase+2k, rbase+2k+1
-    const int nrec = (rb - ra) / 2 + 2;
+    constexpr int RR = RC::RR;
+    const int rbase = ra - RR;                      // record k of the item holds physical rows rbase + RR*k .. + RR-1
+    const int nrec = (rb - ra + RR - 1) / RR + 2;
 
     auto issue = [&](int k) {        // one elected lane: the two TMA boxes of record k
+#ifdef RISP_FUSED_DEBUG
+      if (a.dbg & 2) return;
+#endif
       const unsigned g = gcount + (unsigned)k;
       const uint32_t rec = ring + (g & (D - 1)) * RC::RECB, bar = bars + (g & (D - 1)) * 8;
       const bool has_gt = (MODE != MODE_FWD) && (k >= 1) && (k < nrec - 1);
-      mbar_expect_tx(bar, 2u * RC::RAWROWB + (has_gt ? (uint32_t)RC::GTB : 0u));
-      tma_load_3d(rec, &tm_raw, c0s - kPad, rbase + 2 * k, n, bar);
-      if (has_gt) tma_load_3d(rec + RC::RAWB, &tm_gt, c0s, rbase + 2 * k, 3 * n, bar);
+      mbar_expect_tx(bar, (uint32_t)(RR * RC::RAWROWB) + (has_gt ? (uint32_t)RC::GTB : 0u));
+      tma_load_3d(rec, &tm_raw, c0s - kPad, rbase + RR * k, n, bar);
+      if (has_gt) tma_load_3d(rec + RC::RAWB, &tm_gt, c0s, rbase + RR * k, 3 * n, bar);
     };
     auto wait_rec = [&](int k) {
+#ifdef RISP_FUSED_DEBUG
+      if (a.dbg & 2) return;
+#endif
       const unsigned g = gcount + (unsigned)k;
       mbar_wait(bars + (g & (D - 1)) * 8, (g / D) & 1u);
     };
     // shared-memory address of physical raw row q (reflect-101 at the frame border) -- uniform
     auto row_addr = [&](int q) -> uint32_t {
       const int qq = reflect101(q, H);
-      const unsigned g = gcount + (unsigned)((qq - rbase) >> 1);
-      return ring + (g & (D - 1)) * RC::RECB + (uint32_t)(qq & 1) * RC::RAWROWB;
+      const int rel = qq - rbase;
+      const unsigned g = gcount + (unsigned)(rel / RR);
+      return ring + (g & (D - 1)) * RC::RECB + (uint32_t)(rel % RR) * RC::RAWROWB;
     };
     if (elect_one()) {
       for (int k = 0; k < D && k < nrec; ++k) issue(k);
@@ -440,30 +468,40 @@ fused_kernel(FusedArgs a, ChainDesc d, const __grid_constant__ CUtensorMap tm_ra
     wait_rec(0);
     wait_rec(1);
 
-    // lane offsets inside a raw row (bytes): own 4 columns, left / right halo with the frame border folded in
+    // lane offsets inside a raw row (bytes): own 4 columns; the strip's first / last lane reads its outer halo from the
+    // record (frame border folded into the offset), every other lane gets it from its neighbour by shuffle
     const uint32_t own = (uint32_t)(kPad + lane * 4) * 4u;
+    const bool endL = (lane == 0), endR = (lane == 31) || last;
     const uint32_t oL0 = own + (first ? (HL == 1 ? 4 : 8) : -4 * HL);    // column c0-HL   (reflect: -1 -> 1, -2 -> 2)
     const uint32_t oL1 = own + (first ? 4 : -4);                         // column c0-1    (HL == 2 only)
     const uint32_t oR0 = own + (last ? 8 : 16);                          // column c0+4    (reflect: W -> W-2)
     const uint32_t oR1 = own + (last ? 4 : 20);                          // column c0+5    (reflect: W+1 -> W-3)
 
-    // one row: read the window and the GT row, demosaic, chain, store
-    auto do_row = [&](auto odd_tag, int r, const uint32_t* wa, uint32_t gta) {
-      constexpr bool ODD = decltype(odd_tag)::value;
-      float w[WR][WC];
-#pragma unroll
-      for (int j = 0; j < WR; ++j) {
-        const float4 v = lds4(wa[j] + own);
-        if constexpr (HL == 1) {
-          w[j][0] = lds1(wa[j] + oL0); w[j][1] = v.x; w[j][2] = v.y; w[j][3] = v.z; w[j][4] = v.w; w[j][5] = lds1(wa[j] + oR0);
-        } else {
-          w[j][0] = lds1(wa[j] + oL0); w[j][1] = lds1(wa[j] + oL1);
-          w[j][2] = v.x; w[j][3] = v.y; w[j][4] = v.z; w[j][5] = v.w;
-          w[j][6] = lds1(wa[j] + oR0); w[j][7] = lds1(wa[j] + oR1);
-        }
+    float w[WR + 1][WC];                                        // raw rows r-HL .. r+1+HL of the current row pair
+    auto load_row = [&](int jw, uint32_t ra_) {                // one raw row of the window: columns c0-HL .. c0+3+HL
+      float* dst = w[jw];
+      const unsigned full = 0xffffffffu;
+      const float4 v = lds4(ra_ + own);
+      if constexpr (HL == 1) {
+        float l = __shfl_up_sync(full, v.w, 1), r = __shfl_down_sync(full, v.x, 1);
+        if (endL) l = lds1(ra_ + oL0);
+        if (endR) r = lds1(ra_ + oR0);
+        dst[0] = l; dst[1] = v.x; dst[2] = v.y; dst[3] = v.z; dst[4] = v.w; dst[5] = r;
+      } else {
+        float l0 = __shfl_up_sync(full, v.z, 1), l1 = __shfl_up_sync(full, v.w, 1);
+        float r0 = __shfl_down_sync(full, v.x, 1), r1 = __shfl_down_sync(full, v.y, 1);
+        if (endL) { l0 = lds1(ra_ + oL0); l1 = lds1(ra_ + oL1); }
+        if (endR) { r0 = lds1(ra_ + oR0); r1 = lds1(ra_ + oR1); }
+        dst[0] = l0; dst[1] = l1; dst[2] = v.x; dst[3] = v.y; dst[4] = v.z; dst[5] = v.w; dst[6] = r0; dst[7] = r1;
       }
+    };
+
+    // one row from the register window w[RO .. RO+WR): demosaic, chain (+ loss and backward), store
+    auto do_row = [&](auto ro_tag, auto odd_tag, int r, uint32_t gta) {
+      constexpr int RO = decltype(ro_tag)::value;
+      constexpr bool ODD = decltype(odd_tag)::value;
       P2 lo, hi;
-      demosaic4<DM, HL, 0, ODD, WR>(w, a.clip_hi, lo, hi);
+      demosaic4<DM, HL, RO, ODD, WR + 1>(w, a.clip_hi, lo, hi);
       P2 ylo, yhi;
       if constexpr (MODE == MODE_FWD) {
         ylo = Fwd<SIG, 0>::go(lo, cp, slow);
@@ -471,14 +509,19 @@ fused_kernel(FusedArgs a, ChainDesc d, const __grid_constant__ CUtensorMap tm_ra
       } else {
         float4 tg[3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) tg[c] = lds4(gta + c * 2 * kStrip * 4 + lane * 16);
+        for (int c = 0; c < 3; ++c) tg[c] = lds4(gta + c * RC::GTPLANEB + lane * 16);
         P2 tlo, thi;
         tlo.b = make_float2(tg[0].x, tg[0].y); tlo.g = make_float2(tg[1].x, tg[1].y); tlo.r = make_float2(tg[2].x, tg[2].y);
         thi.b = make_float2(tg[0].z, tg[0].w); thi.g = make_float2(tg[1].z, tg[1].w); thi.r = make_float2(tg[2].z, tg[2].w);
         Run<SIG, 0, MODE>::go(lo, tlo, cp, acc, loss, ylo, slow, lane_w);
         Run<SIG, 0, MODE>::go(hi, thi, cp, acc, loss, yhi, slow, lane_w);
       }
-      if ((MODE == MODE_FWD || yb) && active) {
+#ifdef RISP_FUSED_DEBUG
+      const bool st_ok = !(a.dbg & 1) || ylo.b.x == 12345.678f;
+#else
+      constexpr bool st_ok = true;
+#endif
+      if ((MODE == MODE_FWD || yb) && active && st_ok) {
         float* po = yb + (size_t)r * W + c0;
         st_stream4(po, make_float4(ylo.b.x, ylo.b.y, yhi.b.x, yhi.b.y));
         st_stream4(po + plane, make_float4(ylo.g.x, ylo.g.y, yhi.g.x, yhi.g.y));
@@ -486,28 +529,45 @@ fused_kernel(FusedArgs a, ChainDesc d, const __grid_constant__ CUtensorMap tm_ra
       }
     };
 
-    // iteration m computes rows r = ra + 2(m-1) (even) and r+1 (odd) from records m-1, m, m+1
+    // iteration m computes the RR rows of record m (pairs of an even and an odd row) from records m-1, m, m+1
     for (int m = 1; m < nrec - 1; ++m) {
-      const int r = ra + 2 * (m - 1);
+      const int R0 = ra + RR * (m - 1);
       wait_rec(m + 1);
       const unsigned gB = gcount + (unsigned)m;
       const uint32_t recA = ring + ((gB - 1) & (D - 1)) * RC::RECB, recB = ring + (gB & (D - 1)) * RC::RECB,
                      recC = ring + ((gB + 1) & (D - 1)) * RC::RECB;
-      uint32_t we[WR], wo[WR];
-      if (r >= HL && r + 1 + HL < H) {           // interior: static places
-        if constexpr (HL == 1) {
-          we[0] = recA + RC::RAWROWB; we[1] = recB; we[2] = recB + RC::RAWROWB;
-          wo[0] = recB; wo[1] = recB + RC::RAWROWB; wo[2] = recC;
-        } else {
-          we[0] = recA; we[1] = recA + RC::RAWROWB; we[2] = recB; we[3] = recB + RC::RAWROWB; we[4] = recC;
-          wo[0] = recA + RC::RAWROWB; wo[1] = recB; wo[2] = recB + RC::RAWROWB; wo[3] = recC; wo[4] = recC + RC::RAWROWB;
-        }
-      } else {                                   // first / last rows of the frame: reflected rows
+      const bool interior = (R0 >= HL) && (R0 + RR - 1 + HL < H);
 #pragma unroll
-        for (int j = 0; j < WR; ++j) { we[j] = row_addr(r - HL + j); wo[j] = row_addr(r + 1 - HL + j); }
+      for (int p = 0; p < RR / 2; ++p) {
+        const int r = R0 + 2 * p;
+        if (r < rb) {
+          uint32_t wa[WR + 1];
+#pragma unroll
+          for (int j = 0; j < WR + 1; ++j) {
+            const int idx = 2 * p - HL + j;          // row of the window relative to record m (static)
+            wa[j] = (idx < 0) ? recA + (uint32_t)(RR + idx) * RC::RAWROWB
+                  : (idx >= RR) ? recC + (uint32_t)(idx - RR) * RC::RAWROWB : recB + (uint32_t)idx * RC::RAWROWB;
+          }
+          if (!interior) {                           // first / last rows of the frame: reflected rows
+#pragma unroll
+            for (int j = 0; j < WR + 1; ++j) wa[j] = row_addr(r - HL + j);
+          }
+          if constexpr (MODE == MODE_FWD) {          // the WR+1 rows are read once and serve both output rows
+#pragma unroll
+            for (int j = 0; j < WR + 1; ++j) load_row(j, wa[j]);
+            do_row(std::integral_constant<int, 0>{}, std::false_type{}, r, 0u);
+            do_row(std::integral_constant<int, 1>{}, std::true_type{}, r + 1, 0u);
+          } else {                                   // register-heavy modes: one window at a time
+            const uint32_t gta = recB + RC::RAWB + (uint32_t)(2 * p) * kStrip * 4;
+#pragma unroll
+            for (int j = 0; j < WR; ++j) load_row(j, wa[j]);
+            do_row(std::integral_constant<int, 0>{}, std::false_type{}, r, gta);
+#pragma unroll
+            for (int j = 0; j < WR; ++j) load_row(j, wa[j + 1]);
+            do_row(std::integral_constant<int, 0>{}, std::true_type{}, r + 1, gta + kStrip * 4);
+          }
+        }
       }
-      do_row(std::false_type{}, r, we, recB + RC::RAWB);
-      do_row(std::true_type{}, r + 1, wo, recB + RC::RAWB + kStrip * 4);
       __syncwarp();                              // every lane has read record m-1: its slot may be refilled
       if (m - 1 + D < nrec) {
         if (elect_one()) issue(m - 1 + D);
@@ -575,20 +635,20 @@ fused_kernel(FusedArgs a, ChainDesc d, const __grid_constant__ CUtensorMap tm_ra
 // ---- host side ---------------------------------------------------------------------------------------------------------
 struct Geometry { int rows_per_chunk, chunks, strip_blocks, cpf, grid; };
 
-static Geometry geometry(int N, int H, int W, int ctas_per_sm) {
+static Geometry geometry(int N, int H, int W, int ctas_per_sm, int rr) {
   Geometry g;
   g.strip_blocks = (int)cdiv(W, kStrip);     // items are (row chunk, strip): one warp per CTA
   const int slots = sm_count() * ctas_per_sm;
   g.cpf = slots / N < 1 ? 1 : slots / N;
   // rows per chunk: minimise rounds * (rows + per-item overhead); an item costs ~3 extra rows (window fill, exposed latency)
   long long best = -1;
-  int best_rows = 2;
-  for (int rows = 2; rows <= 256; rows += 2) {
-    if (rows > H && rows > 2) break;
+  int best_rows = rr;
+  for (int rows = rr; rows <= 256; rows += rr) {        // whole records (rr rows each)
+    if (rows > H && rows > rr) break;
     const int chunks = (int)cdiv(H, rows);
     const long long items = (long long)chunks * g.strip_blocks;
     const long long rounds = cdiv(items, g.cpf);
-    const long long cost = rounds * (rows + 3);
+    const long long cost = rounds * (rows + rr + 2);   // an item also loads a lead-in record and fills the pipeline
     if (best < 0 || cost < best || (cost == best && rows > best_rows)) { best = cost; best_rows = rows; }
   }
   g.rows_per_chunk = best_rows;
@@ -647,13 +707,13 @@ static EncodeTiledFn encode_fn() {
   }
   return fn;
 }
-// fp32 tensor (W, H, Z) with rows of W floats, box (bx, 2, bz); out-of-bounds elements read as zero
-static int make_map(CUtensorMap* tm, const float* base, int W, int H, long long Z, int bx, int bz) {
+// fp32 tensor (W, H, Z) with rows of W floats, box (bx, by, bz); out-of-bounds elements read as zero
+static int make_map(CUtensorMap* tm, const float* base, int W, int H, long long Z, int bx, int by, int bz) {
   EncodeTiledFn fn = encode_fn();
   RISP_REQUIRE(fn, RISP_E_CUDA, "fused pipeline: cuTensorMapEncodeTiled is not available");
   const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Z};
   const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
-  const cuuint32_t box[3] = {(cuuint32_t)bx, 2u, (cuuint32_t)bz};
+  const cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bz};
   const cuuint32_t estr[3] = {1u, 1u, 1u};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -664,14 +724,14 @@ static int make_map(CUtensorMap* tm, const float* base, int W, int H, long long 
 
 template <int DM, int MODE, unsigned SIG>
 static int launch_one(FusedArgs a, const ChainDesc& d, int N, cudaStream_t st, Geometry* gout) {
-  const Geometry g = geometry(N, a.H, a.W, resident_ctas<DM, MODE, SIG>());
+  const Geometry g = geometry(N, a.H, a.W, resident_ctas<DM, MODE, SIG>(), RingCfg<MODE>::RR);
   if (gout) { *gout = g; return RISP_OK; }
   a.rows_per_chunk = g.rows_per_chunk; a.chunks = g.chunks; a.strip_blocks = g.strip_blocks; a.cpf = g.cpf;
   CUtensorMap tm_raw, tm_gt;
-  int rc = make_map(&tm_raw, a.raw, a.W, a.H, N, kStrip + 2 * kPad, 1);
+  int rc = make_map(&tm_raw, a.raw, a.W, a.H, N, kStrip + 2 * kPad, RingCfg<MODE>::RR, 1);
   if (rc != RISP_OK) return rc;
   if (MODE != MODE_FWD) {
-    rc = make_map(&tm_gt, a.gt, a.W, a.H, 3ll * N, kStrip, 3);
+    rc = make_map(&tm_gt, a.gt, a.W, a.H, 3ll * N, kStrip, RingCfg<MODE>::RR, 3);
     if (rc != RISP_OK) return rc;
   } else {
     tm_gt = tm_raw;
@@ -683,7 +743,8 @@ static int launch_one(FusedArgs a, const ChainDesc& d, int N, cudaStream_t st, G
 template <int MODE>
 static int dispatch(const FusedArgs& a, const ChainDesc& d, unsigned sig, int N, int dm_kind, cudaStream_t st, Geometry* gout) {
 #define RISP_F_SIG(DMK, SG) if (sig == (SG)) return launch_one<DMK, MODE, (SG)>(a, d, N, st, gout);
-#define RISP_F_DM(DMK) RISP_F_SIG(DMK, RISP_SIG_A) RISP_F_SIG(DMK, RISP_SIG_B) RISP_F_SIG(DMK, RISP_SIG_C) RISP_F_SIG(DMK, RISP_SIG_D)
+#define RISP_F_DM(DMK) RISP_F_SIG(DMK, RISP_SIG_A) RISP_F_SIG(DMK, RISP_SIG_B) RISP_F_SIG(DMK, RISP_SIG_C) RISP_F_SIG(DMK, RISP_SIG_D) \
+  if constexpr (MODE == MODE_FWD) { RISP_F_SIG(DMK, RISP_SIG_SKIP) }
   switch (dm_kind) {
     case RISP_DM_NEAREST: RISP_F_DM(RISP_DM_NEAREST) break;
     case RISP_DM_BILINEAR: RISP_F_DM(RISP_DM_BILINEAR) break;
@@ -701,7 +762,7 @@ static int dispatch(const FusedArgs& a, const ChainDesc& d, unsigned sig, int N,
 bool fused_handles(const ChainDesc& d, int N, int param_stride, int H, int W) {
   if ((long long)H * W * 3 >= (1ll << 31)) return false;     // 32-bit element offsets inside a frame
   const unsigned sig = chain_signature(d);
-  if (sig != RISP_SIG_A && sig != RISP_SIG_B && sig != RISP_SIG_C && sig != RISP_SIG_D) return false;
+  if (sig != RISP_SIG_A && sig != RISP_SIG_B && sig != RISP_SIG_C && sig != RISP_SIG_D && sig != RISP_SIG_SKIP) return false;
   if (param_stride != 0 && N > fused::kCRows) return false;
   return fused::eff_from_ops(d.op, d.iarg, d.S).ok;
 }
@@ -728,7 +789,8 @@ int fused_launch(int mode, const float* raw, const float* gt, float* y, float* p
   fused_prep_kernel<<<rows, 32, 0, st>>>(params, pstride, d, cbase + (size_t)slot * kCRows * kCRowFloats);
   int rc = check_launch("fused_prep_kernel");
   if (rc != RISP_OK) return rc;
-  FusedArgs a{raw, gt, y, partial, params, pstride, H, W, 0, 0, 0, 0, clip_hi, slot};
+  static const int dbg = getenv("RISP_FUSED_DBG") ? atoi(getenv("RISP_FUSED_DBG")) : 0;
+  FusedArgs a{raw, gt, y, partial, params, pstride, H, W, 0, 0, 0, 0, clip_hi, slot, dbg};
   const unsigned sig = chain_signature(d);
   Geometry g;
   if (mode == 0) return dispatch<MODE_FWD>(a, d, sig, N, dm_kind, st, nullptr);

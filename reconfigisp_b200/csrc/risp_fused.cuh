@@ -36,10 +36,10 @@ __host__ __device__ constexpr int fop_nacc(int op) {    // float2 accumulators o
          : (op == RISP_OP_GTM) ? 4 : 0;
 }
 __host__ __device__ constexpr bool fop_supported(int op) {
-  return op == RISP_OP_GAMMA || op == RISP_OP_GAIN || op == RISP_OP_POLY10 || op == RISP_OP_GTM;
+  return op == RISP_OP_GAMMA || op == RISP_OP_GAIN || op == RISP_OP_POLY10 || op == RISP_OP_GTM || op == RISP_OP_SKIP;
 }
 // output of the stage is guaranteed to lie in [0,1]
-__host__ __device__ constexpr bool fop_out01(int op) { return op != RISP_OP_GAIN; }
+__host__ __device__ constexpr bool fop_out01(int op) { return op != RISP_OP_GAIN && op != RISP_OP_SKIP; }
 
 struct EffChain {
   int n;

@@ -391,8 +391,10 @@ extern "C" int risp_pipeline_fwd(const float* raw, float* y, int N, int H, int W
   if (rc != RISP_OK) return rc;
   RISP_REQUIRE(P == 0 || params, RISP_E_INVALID, "risp_pipeline_fwd: chain needs %d parameters but params is null", P);
   RISP_REQUIRE(param_stride == 0 || param_stride >= P, RISP_E_INVALID, "risp_pipeline_fwd: param_stride %d < %d", param_stride, P);
-  if (S > 0 && use_fused()) {
-    rc = fused_launch(0, raw, nullptr, y, nullptr, params, param_stride, N, H, W, dm_kind, dm_clip_hi, d, as_stream(stream), nullptr);
+  if (use_fused()) {
+    ChainDesc df = d;
+    if (S == 0) { df.S = 1; df.op[0] = RISP_OP_SKIP; df.off[0] = 0; df.iarg[0] = 0; }     // demosaic only
+    rc = fused_launch(0, raw, nullptr, y, nullptr, params, param_stride, N, H, W, dm_kind, dm_clip_hi, df, as_stream(stream), nullptr);
     if (rc != 1) return rc;
   }
   PipeArgs a{raw, nullptr, y, nullptr, params, param_stride, H, W, 0, dm_clip_hi, 0};

@@ -385,6 +385,7 @@ struct Sig {
 #define RISP_SIG_B ::risp::make_sig(RISP_OP_GAMMA, RISP_OP_POLY10, RISP_OP_GAIN)
 #define RISP_SIG_C ::risp::make_sig(RISP_OP_GAMMA, RISP_OP_POLY10)
 #define RISP_SIG_D ::risp::make_sig(RISP_OP_GAMMA, RISP_OP_GTM)
+#define RISP_SIG_SKIP ::risp::make_sig(RISP_OP_SKIP)     // demosaic only (fused kernels)
 #define RISP_FOR_EACH_CHAIN_SIG(X) X(RISP_SIG_A) X(RISP_SIG_B) X(RISP_SIG_C) X(RISP_SIG_D)
 #define RISP_FOR_EACH_SINGLE_SIG(X)                                                                          \
   X(::risp::make_sig(RISP_OP_GAMMA)) X(::risp::make_sig(RISP_OP_GAIN)) X(::risp::make_sig(RISP_OP_GAIN_CLIP)) \
