@@ -477,100 +477,182 @@ fused_kernel(FusedArgs a, ChainDesc d, const __grid_constant__ CUtensorMap tm_ra
     const uint32_t oR0 = own + (last ? 8 : 16);                          // column c0+4    (reflect: W -> W-2)
     const uint32_t oR1 = own + (last ? 4 : 20);                          // column c0+5    (reflect: W+1 -> W-3)
 
-    float w[WR + 1][WC];                                        // raw rows r-HL .. r+1+HL of the current row pair
-    auto load_row = [&](int jw, uint32_t ra_) {                // one raw row of the window: columns c0-HL .. c0+3+HL
-      float* dst = w[jw];
-      const unsigned full = 0xffffffffu;
-      const float4 v = lds4(ra_ + own);
-      if constexpr (HL == 1) {
-        float l = __shfl_up_sync(full, v.w, 1), r = __shfl_down_sync(full, v.x, 1);
-        if (endL) l = lds1(ra_ + oL0);
-        if (endR) r = lds1(ra_ + oR0);
-        dst[0] = l; dst[1] = v.x; dst[2] = v.y; dst[3] = v.z; dst[4] = v.w; dst[5] = r;
-      } else {
-        float l0 = __shfl_up_sync(full, v.z, 1), l1 = __shfl_up_sync(full, v.w, 1);
-        float r0 = __shfl_down_sync(full, v.x, 1), r1 = __shfl_down_sync(full, v.y, 1);
-        if (endL) { l0 = lds1(ra_ + oL0); l1 = lds1(ra_ + oL1); }
-        if (endR) { r0 = lds1(ra_ + oR0); r1 = lds1(ra_ + oR1); }
-        dst[0] = l0; dst[1] = l1; dst[2] = v.x; dst[3] = v.y; dst[4] = v.z; dst[5] = v.w; dst[6] = r0; dst[7] = r1;
-      }
-    };
-
-    // one row from the register window w[RO .. RO+WR): demosaic, chain (+ loss and backward), store
-    auto do_row = [&](auto ro_tag, auto odd_tag, int r, uint32_t gta) {
-      constexpr int RO = decltype(ro_tag)::value;
-      constexpr bool ODD = decltype(odd_tag)::value;
-      P2 lo, hi;
-      demosaic4<DM, HL, RO, ODD, WR + 1>(w, a.clip_hi, lo, hi);
-      P2 ylo, yhi;
-      if constexpr (MODE == MODE_FWD) {
-        ylo = Fwd<SIG, 0>::go(lo, cp, slow);
-        yhi = Fwd<SIG, 0>::go(hi, cp, slow);
-      } else {
-        float4 tg[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) tg[c] = lds4(gta + c * RC::GTPLANEB + lane * 16);
-        P2 tlo, thi;
-        tlo.b = make_float2(tg[0].x, tg[0].y); tlo.g = make_float2(tg[1].x, tg[1].y); tlo.r = make_float2(tg[2].x, tg[2].y);
-        thi.b = make_float2(tg[0].z, tg[0].w); thi.g = make_float2(tg[1].z, tg[1].w); thi.r = make_float2(tg[2].z, tg[2].w);
-        Run<SIG, 0, MODE>::go(lo, tlo, cp, acc, loss, ylo, slow, lane_w);
-        Run<SIG, 0, MODE>::go(hi, thi, cp, acc, loss, yhi, slow, lane_w);
-      }
-#ifdef RISP_FUSED_DEBUG
-      const bool st_ok = !(a.dbg & 1) || ylo.b.x == 12345.678f;
-#else
-      constexpr bool st_ok = true;
-#endif
-      if ((MODE == MODE_FWD || yb) && active && st_ok) {
-        float* po = yb + (size_t)r * W + c0;
-        st_stream4(po, make_float4(ylo.b.x, ylo.b.y, yhi.b.x, yhi.b.y));
-        st_stream4(po + plane, make_float4(ylo.g.x, ylo.g.y, yhi.g.x, yhi.g.y));
-        st_stream4(po + 2 * plane, make_float4(ylo.r.x, ylo.r.y, yhi.r.x, yhi.r.y));
-      }
-    };
-
-    // iteration m computes the RR rows of record m (pairs of an even and an odd row) from records m-1, m, m+1
-    for (int m = 1; m < nrec - 1; ++m) {
-      const int R0 = ra + RR * (m - 1);
-      wait_rec(m + 1);
-      const unsigned gB = gcount + (unsigned)m;
-      const uint32_t recA = ring + ((gB - 1) & (D - 1)) * RC::RECB, recB = ring + (gB & (D - 1)) * RC::RECB,
-                     recC = ring + ((gB + 1) & (D - 1)) * RC::RECB;
-      const bool interior = (R0 >= HL) && (R0 + RR - 1 + HL < H);
-#pragma unroll
-      for (int p = 0; p < RR / 2; ++p) {
-        const int r = R0 + 2 * p;
-        if (r < rb) {
-          uint32_t wa[WR + 1];
-#pragma unroll
-          for (int j = 0; j < WR + 1; ++j) {
-            const int idx = 2 * p - HL + j;          // row of the window relative to record m (static)
-            wa[j] = (idx < 0) ? recA + (uint32_t)(RR + idx) * RC::RAWROWB
-                  : (idx >= RR) ? recC + (uint32_t)(idx - RR) * RC::RAWROWB : recB + (uint32_t)idx * RC::RAWROWB;
-          }
-          if (!interior) {                           // first / last rows of the frame: reflected rows
-#pragma unroll
-            for (int j = 0; j < WR + 1; ++j) wa[j] = row_addr(r - HL + j);
-          }
-          if constexpr (MODE == MODE_FWD) {          // the WR+1 rows are read once and serve both output rows
-#pragma unroll
-            for (int j = 0; j < WR + 1; ++j) load_row(j, wa[j]);
-            do_row(std::integral_constant<int, 0>{}, std::false_type{}, r, 0u);
-            do_row(std::integral_constant<int, 1>{}, std::true_type{}, r + 1, 0u);
-          } else {                                   // register-heavy modes: one window at a time
-            const uint32_t gta = recB + RC::RAWB + (uint32_t)(2 * p) * kStrip * 4;
-#pragma unroll
-            for (int j = 0; j < WR; ++j) load_row(j, wa[j]);
-            do_row(std::integral_constant<int, 0>{}, std::false_type{}, r, gta);
-#pragma unroll
-            for (int j = 0; j < WR; ++j) load_row(j, wa[j + 1]);
-            do_row(std::integral_constant<int, 0>{}, std::true_type{}, r + 1, gta + kStrip * 4);
+    if constexpr (MODE != MODE_FWD) {
+      // ---- backward-carrying kernels (issue-bound): 2-row records, a private window per row read with plain LDS ----
+      // one row: read the window and the GT row, demosaic, chain, store
+      auto do_row = [&](auto odd_tag, int r, const uint32_t* wa, uint32_t gta) {
+        constexpr bool ODD = decltype(odd_tag)::value;
+        float w[WR][WC];
+  #pragma unroll
+        for (int j = 0; j < WR; ++j) {
+          const float4 v = lds4(wa[j] + own);
+          if constexpr (HL == 1) {
+            w[j][0] = lds1(wa[j] + oL0); w[j][1] = v.x; w[j][2] = v.y; w[j][3] = v.z; w[j][4] = v.w; w[j][5] = lds1(wa[j] + oR0);
+          } else {
+            w[j][0] = lds1(wa[j] + oL0); w[j][1] = lds1(wa[j] + oL1);
+            w[j][2] = v.x; w[j][3] = v.y; w[j][4] = v.z; w[j][5] = v.w;
+            w[j][6] = lds1(wa[j] + oR0); w[j][7] = lds1(wa[j] + oR1);
           }
         }
+        P2 lo, hi;
+        demosaic4<DM, HL, 0, ODD, WR>(w, a.clip_hi, lo, hi);
+        P2 ylo, yhi;
+        if constexpr (MODE == MODE_FWD) {
+          ylo = Fwd<SIG, 0>::go(lo, cp, slow);
+          yhi = Fwd<SIG, 0>::go(hi, cp, slow);
+        } else {
+          float4 tg[3];
+  #pragma unroll
+          for (int c = 0; c < 3; ++c) tg[c] = lds4(gta + c * RC::GTPLANEB + lane * 16);
+          P2 tlo, thi;
+          tlo.b = make_float2(tg[0].x, tg[0].y); tlo.g = make_float2(tg[1].x, tg[1].y); tlo.r = make_float2(tg[2].x, tg[2].y);
+          thi.b = make_float2(tg[0].z, tg[0].w); thi.g = make_float2(tg[1].z, tg[1].w); thi.r = make_float2(tg[2].z, tg[2].w);
+          Run<SIG, 0, MODE>::go(lo, tlo, cp, acc, loss, ylo, slow, lane_w);
+          Run<SIG, 0, MODE>::go(hi, thi, cp, acc, loss, yhi, slow, lane_w);
+        }
+        if ((MODE == MODE_FWD || yb) && active) {
+          float* po = yb + (size_t)r * W + c0;
+          st_stream4(po, make_float4(ylo.b.x, ylo.b.y, yhi.b.x, yhi.b.y));
+          st_stream4(po + plane, make_float4(ylo.g.x, ylo.g.y, yhi.g.x, yhi.g.y));
+          st_stream4(po + 2 * plane, make_float4(ylo.r.x, ylo.r.y, yhi.r.x, yhi.r.y));
+        }
+      };
+
+      // iteration m computes rows r = ra + 2(m-1) (even) and r+1 (odd) from records m-1, m, m+1
+      for (int m = 1; m < nrec - 1; ++m) {
+        const int r = ra + 2 * (m - 1);
+        wait_rec(m + 1);
+        const unsigned gB = gcount + (unsigned)m;
+        const uint32_t recA = ring + ((gB - 1) & (D - 1)) * RC::RECB, recB = ring + (gB & (D - 1)) * RC::RECB,
+                       recC = ring + ((gB + 1) & (D - 1)) * RC::RECB;
+        uint32_t we[WR], wo[WR];
+        if (r >= HL && r + 1 + HL < H) {           // interior: static places
+          if constexpr (HL == 1) {
+            we[0] = recA + RC::RAWROWB; we[1] = recB; we[2] = recB + RC::RAWROWB;
+            wo[0] = recB; wo[1] = recB + RC::RAWROWB; wo[2] = recC;
+          } else {
+            we[0] = recA; we[1] = recA + RC::RAWROWB; we[2] = recB; we[3] = recB + RC::RAWROWB; we[4] = recC;
+            wo[0] = recA + RC::RAWROWB; wo[1] = recB; wo[2] = recB + RC::RAWROWB; wo[3] = recC; wo[4] = recC + RC::RAWROWB;
+          }
+        } else {                                   // first / last rows of the frame: reflected rows
+  #pragma unroll
+          for (int j = 0; j < WR; ++j) { we[j] = row_addr(r - HL + j); wo[j] = row_addr(r + 1 - HL + j); }
+        }
+        do_row(std::false_type{}, r, we, recB + RC::RAWB);
+        do_row(std::true_type{}, r + 1, wo, recB + RC::RAWB + kStrip * 4);
+        __syncwarp();                              // every lane has read record m-1: its slot may be refilled
+        if (m - 1 + D < nrec) {
+          if (elect_one()) issue(m - 1 + D);
+        }
       }
-      __syncwarp();                              // every lane has read record m-1: its slot may be refilled
-      if (m - 1 + D < nrec) {
-        if (elect_one()) issue(m - 1 + D);
+    } else {
+      // ---- inference kernel (memory-bound): RR-row records, one shared window per row pair, halo by shuffle ---------
+      float w[WR + 1][WC];                                        // raw rows r-HL .. r+1+HL of the current row pair
+      auto load_row = [&](float* dst, uint32_t ra_) {            // one raw row of the window: columns c0-HL .. c0+3+HL
+        const unsigned full = 0xffffffffu;
+        const float4 v = lds4(ra_ + own);
+        if constexpr (MODE != MODE_FWD) {
+          // issue-bound kernels: every lane reads its halo columns from the record (a 4-way bank conflict costs nothing here,
+          // two shuffles and two selects per row do)
+          if constexpr (HL == 1) {
+            dst[0] = lds1(ra_ + oL0); dst[1] = v.x; dst[2] = v.y; dst[3] = v.z; dst[4] = v.w; dst[5] = lds1(ra_ + oR0);
+          } else {
+            dst[0] = lds1(ra_ + oL0); dst[1] = lds1(ra_ + oL1); dst[2] = v.x; dst[3] = v.y; dst[4] = v.z; dst[5] = v.w;
+            dst[6] = lds1(ra_ + oR0); dst[7] = lds1(ra_ + oR1);
+          }
+        } else if constexpr (HL == 1) {
+          float l = __shfl_up_sync(full, v.w, 1), r = __shfl_down_sync(full, v.x, 1);
+          if (endL) l = lds1(ra_ + oL0);
+          if (endR) r = lds1(ra_ + oR0);
+          dst[0] = l; dst[1] = v.x; dst[2] = v.y; dst[3] = v.z; dst[4] = v.w; dst[5] = r;
+        } else {
+          float l0 = __shfl_up_sync(full, v.z, 1), l1 = __shfl_up_sync(full, v.w, 1);
+          float r0 = __shfl_down_sync(full, v.x, 1), r1 = __shfl_down_sync(full, v.y, 1);
+          if (endL) { l0 = lds1(ra_ + oL0); l1 = lds1(ra_ + oL1); }
+          if (endR) { r0 = lds1(ra_ + oR0); r1 = lds1(ra_ + oR1); }
+          dst[0] = l0; dst[1] = l1; dst[2] = v.x; dst[3] = v.y; dst[4] = v.z; dst[5] = v.w; dst[6] = r0; dst[7] = r1;
+        }
+      };
+
+      // one row from the register window w[RO .. RO+WR): demosaic, chain (+ loss and backward), store
+      auto do_row = [&](auto ro_tag, auto odd_tag, int r, uint32_t gta, const uint32_t* wa) {
+        constexpr int RO = decltype(ro_tag)::value;
+        constexpr bool ODD = decltype(odd_tag)::value;
+        P2 lo, hi;
+        if constexpr (MODE == MODE_FWD) {
+          demosaic4<DM, HL, RO, ODD, WR + 1>(w, a.clip_hi, lo, hi);
+        } else {                                     // register-heavy modes: a private window, dead before the chain starts
+          float wl[WR][WC];
+  #pragma unroll
+          for (int j = 0; j < WR; ++j) load_row(wl[j], wa[j]);
+          demosaic4<DM, HL, 0, ODD, WR>(wl, a.clip_hi, lo, hi);
+        }
+        P2 ylo, yhi;
+        if constexpr (MODE == MODE_FWD) {
+          ylo = Fwd<SIG, 0>::go(lo, cp, slow);
+          yhi = Fwd<SIG, 0>::go(hi, cp, slow);
+        } else {
+          float4 tg[3];
+  #pragma unroll
+          for (int c = 0; c < 3; ++c) tg[c] = lds4(gta + c * RC::GTPLANEB + lane * 16);
+          P2 tlo, thi;
+          tlo.b = make_float2(tg[0].x, tg[0].y); tlo.g = make_float2(tg[1].x, tg[1].y); tlo.r = make_float2(tg[2].x, tg[2].y);
+          thi.b = make_float2(tg[0].z, tg[0].w); thi.g = make_float2(tg[1].z, tg[1].w); thi.r = make_float2(tg[2].z, tg[2].w);
+          Run<SIG, 0, MODE>::go(lo, tlo, cp, acc, loss, ylo, slow, lane_w);
+          Run<SIG, 0, MODE>::go(hi, thi, cp, acc, loss, yhi, slow, lane_w);
+        }
+  #ifdef RISP_FUSED_DEBUG
+        const bool st_ok = !(a.dbg & 1) || ylo.b.x == 12345.678f;
+  #else
+        constexpr bool st_ok = true;
+  #endif
+        if ((MODE == MODE_FWD || yb) && active && st_ok) {
+          float* po = yb + (size_t)r * W + c0;
+          st_stream4(po, make_float4(ylo.b.x, ylo.b.y, yhi.b.x, yhi.b.y));
+          st_stream4(po + plane, make_float4(ylo.g.x, ylo.g.y, yhi.g.x, yhi.g.y));
+          st_stream4(po + 2 * plane, make_float4(ylo.r.x, ylo.r.y, yhi.r.x, yhi.r.y));
+        }
+      };
+
+      // iteration m computes the RR rows of record m (pairs of an even and an odd row) from records m-1, m, m+1
+      for (int m = 1; m < nrec - 1; ++m) {
+        const int R0 = ra + RR * (m - 1);
+        wait_rec(m + 1);
+        const unsigned gB = gcount + (unsigned)m;
+        const uint32_t recA = ring + ((gB - 1) & (D - 1)) * RC::RECB, recB = ring + (gB & (D - 1)) * RC::RECB,
+                       recC = ring + ((gB + 1) & (D - 1)) * RC::RECB;
+        const bool interior = (R0 >= HL) && (R0 + RR - 1 + HL < H);
+  #pragma unroll
+        for (int p = 0; p < RR / 2; ++p) {
+          const int r = R0 + 2 * p;
+          if (r < rb) {
+            uint32_t wa[WR + 1];
+  #pragma unroll
+            for (int j = 0; j < WR + 1; ++j) {
+              const int idx = 2 * p - HL + j;          // row of the window relative to record m (static)
+              wa[j] = (idx < 0) ? recA + (uint32_t)(RR + idx) * RC::RAWROWB
+                    : (idx >= RR) ? recC + (uint32_t)(idx - RR) * RC::RAWROWB : recB + (uint32_t)idx * RC::RAWROWB;
+            }
+            if (!interior) {                           // first / last rows of the frame: reflected rows
+  #pragma unroll
+              for (int j = 0; j < WR + 1; ++j) wa[j] = row_addr(r - HL + j);
+            }
+            if constexpr (MODE == MODE_FWD) {          // the WR+1 rows are read once and serve both output rows
+  #pragma unroll
+              for (int j = 0; j < WR + 1; ++j) load_row(w[j], wa[j]);
+              do_row(std::integral_constant<int, 0>{}, std::false_type{}, r, 0u, wa);
+              do_row(std::integral_constant<int, 1>{}, std::true_type{}, r + 1, 0u, wa);
+            } else {                                   // register-heavy modes: one window at a time
+              const uint32_t gta = recB + RC::RAWB + (uint32_t)(2 * p) * kStrip * 4;
+              do_row(std::integral_constant<int, 0>{}, std::false_type{}, r, gta, wa);
+              do_row(std::integral_constant<int, 0>{}, std::true_type{}, r + 1, gta + kStrip * 4, wa + 1);
+            }
+          }
+        }
+        __syncwarp();                              // every lane has read record m-1: its slot may be refilled
+        if (m - 1 + D < nrec) {
+          if (elect_one()) issue(m - 1 + D);
+        }
       }
     }
     gcount += (unsigned)nrec;
