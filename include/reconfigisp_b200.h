@@ -40,6 +40,9 @@ enum risp_status {
 int risp_abi_version(void);
 const char* risp_last_error(void);
 int risp_sm_count(void);
+/* number of kernels this library has launched (or recorded into a CUDA graph being captured) so far in this process;
+ * bench.py reports launches per step from it */
+long long risp_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------
  * Per-pixel stage chain on BGR planes.

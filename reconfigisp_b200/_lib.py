@@ -25,9 +25,9 @@ def parse_header(path=HEADER):
     src = open(path).read()
     src = re.sub(r'/\*.*?\*/', ' ', src, flags=re.S)
     protos = {}
-    for m in re.finditer(r'\b(int|size_t|const char\s*\*)\s+(risp_\w+)\s*\(([^;{]*?)\)\s*;', src, flags=re.S):
+    for m in re.finditer(r'\b(long long|int|size_t|const char\s*\*)\s+(risp_\w+)\s*\(([^;{]*?)\)\s*;', src, flags=re.S):
         ret, name, args = m.group(1), m.group(2), ' '.join(m.group(3).split())
-        restype = {'int': ctypes.c_int, 'size_t': ctypes.c_size_t}.get(ret, ctypes.c_char_p)
+        restype = {'int': ctypes.c_int, 'size_t': ctypes.c_size_t, 'long long': ctypes.c_longlong}.get(ret, ctypes.c_char_p)
         argl = []
         if args and args != 'void':
             for a in args.split(','):
@@ -105,6 +105,10 @@ def ptr(t):
         raise RuntimeError('reconfigisp_b200 ops run on CUDA tensors only (no CPU fallback); got a %s tensor' % t.device)
     if not t.is_contiguous():
         raise ValueError('reconfigisp_b200 ops need contiguous tensors')
+    if t.device.index != torch.cuda.current_device():
+        # kernels are enqueued on the CURRENT device's stream: a tensor of another GPU would be an illegal access
+        raise RuntimeError('tensor lives on cuda:%d but the current device is cuda:%d; wrap the call in torch.cuda.device(t.device)'
+                           % (t.device.index, torch.cuda.current_device()))
     return ctypes.c_void_p(t.data_ptr())
 
 

@@ -16,7 +16,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+
 int check_launch(const char* what) {
+  ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));
@@ -211,4 +214,5 @@ extern "C" {
 int risp_abi_version(void) { return RISP_ABI_VERSION; }
 const char* risp_last_error(void) { return risp::g_err; }
 int risp_sm_count(void) { return risp::sm_count(); }
+long long risp_launch_count(void) { return (long long)risp::g_launches; }
 }

@@ -49,6 +49,40 @@ def allreduce_mean_flat(tensors):
     return out
 
 
+def allreduce_mean_(flat):
+    """In-place average of one contiguous gradient buffer across ranks: a single collective, nothing else."""
+    if is_dist():
+        if dist.get_backend() == 'nccl':
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        else:                                   # gloo (CPU tests) has no AVG
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            flat /= dist.get_world_size()
+    return flat
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off BEFORE it allocates pinned host buffers, so that
+    the H2D copies of 8 ranks do not all stream out of one socket's DRAM (e2e scaling).  Best effort: returns the node or None."""
+    try:
+        import torch.cuda as tc
+        prop = tc.get_device_properties(local_rank)
+        bus = '%04x:%02x:%02x.0' % (getattr(prop, 'pci_domain_id', 0), prop.pci_bus_id, prop.pci_device_id)
+        node = int(open('/sys/bus/pci/devices/%s/numa_node' % bus).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open('/sys/devices/system/node/node%d/cpulist' % node).read().strip().split(','):
+            a, _, b = part.partition('-')
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def shard_batch(n_items, rank, world):
     """Per-rank slice of a batch: batch_size // world_size items each (data/__init__.py:15-16)."""
     per = n_items // world

@@ -42,6 +42,14 @@ class IspModel:
             self.optimizer_G = torch.optim.Adam([p for p in self.netG.trainable_parameters], t['lr_G'], (t['beta1'], t['beta2']),
                                                 capturable=self.use_graph, fused=self.use_graph)
             self._graph, self._graph_key, self._eager_steps = None, None, 0
+            # all trainable gradients are views of ONE flat buffer: zeroing is one kernel and the data-parallel exchange is
+            # one in-place all-reduce (no cat / div / per-tensor copies; codes/models/darts_model.py:31,173 use a DDP bucket)
+            ps = [p for p in self.netG.trainable_parameters if p.numel() > 0]
+            self._flat_grad = torch.zeros(sum(p.numel() for p in ps), device=self.device, dtype=torch.float32)
+            o = 0
+            for p in ps:
+                p.grad = self._flat_grad[o:o + p.numel()].view_as(p)
+                o += p.numel()
             self.optimizers.append(self.optimizer_G)
             if t.get('lr_scheme', 'MultiStepLR') == 'MultiStepLR':
                 self.schedulers.append(torch.optim.lr_scheduler.MultiStepLR(self.optimizer_G, t['lr_steps'], t['lr_gamma']))
@@ -51,7 +59,13 @@ class IspModel:
 
     # -- data ------------------------------------------------------------------------------------------------
     def feed_data(self, data):
-        """(img, gt[, val_img, val_gt]) host or device tensors; pinned host tensors copy asynchronously."""
+        """(img, gt[, val_img, val_gt]) host or device tensors.
+
+        Host tensors are copied on a side stream into one of TWO persistent device buffer sets (alternating), and integer
+        sensor / display codes are decoded there as well, so the copy of batch k+1 overlaps the step of batch k when the
+        caller feeds the next batch before reading the loss:  optimize_parameters(); feed_data(next); loss.item().
+        The step waits for its own batch's copy (event), and a buffer set is not overwritten before the step that read it
+        has finished -- the plain feed_data(); optimize_parameters() order of the reference keeps working unchanged."""
         if len(data) == 2:
             img, gt = data
         elif len(data) == 4:
@@ -60,9 +74,40 @@ class IspModel:
             self.val_gt = val_gt.to(self.device, non_blocking=True)
         else:
             raise ValueError('Invalid data format.')
-        self.img = self._to_device('img', img, self.opt.get('raw_white_level', 1023.))
-        self.gt = self._to_device('gt', gt, 255.)
+        st = self.__dict__.setdefault('_feed', {'parity': 0, 'stream': torch.cuda.Stream(), 'copied': [None, None],
+                                                'used': [None, None]})
+        on_host = not (img.is_cuda and gt.is_cuda)
+        if on_host:
+            b = st['parity'] = 1 - st['parity']
+            cur = torch.cuda.current_stream()
+            if st['used'][b] is not None:
+                st['stream'].wait_event(st['used'][b])        # the step that last read this buffer set is done
+            st['stream'].wait_stream(cur) if st['copied'][b] is None else None
+            with torch.cuda.stream(st['stream']):
+                self.img = self._to_device('img%d' % b, img, self.opt.get('raw_white_level', 1023.))
+                self.gt = self._to_device('gt%d' % b, gt, 255.)
+                ev = torch.cuda.Event()
+                ev.record(st['stream'])
+            st['copied'][b] = ev
+            self._pending = (b, ev)
+        else:
+            self.img = self._to_device('img', img, self.opt.get('raw_white_level', 1023.))
+            self.gt = self._to_device('gt', gt, 255.)
+            self._pending = None
         self._output = None
+
+    def _sync_feed(self):
+        """Make the current stream wait for the copy of the batch it is about to read."""
+        pend = getattr(self, '_pending', None)
+        if pend is not None:
+            torch.cuda.current_stream().wait_event(pend[1])
+
+    def _mark_used(self):
+        pend = getattr(self, '_pending', None)
+        if pend is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self._feed['used'][pend[0]] = ev
 
     def _to_device(self, slot, t, denom):
         """fp32 tensors are copied as they are (the reference's contract); integer sensor / display codes
@@ -97,9 +142,10 @@ class IspModel:
     def optimize_parameters(self):
         """isp_model.py:132-141.  Eager for the first two calls (allocator / optimizer-state warm-up), then the fused
         step is captured into a CUDA graph and replayed for as long as buffers, shapes and learning rates stay put."""
-        if self.use_graph and self._graph_replay():
-            return
-        self._step_eager()
+        self._sync_feed()
+        if not (self.use_graph and self._graph_replay()):
+            self._step_eager()
+        self._mark_used()
 
     def _graph_signature(self):
         return (self.img.data_ptr(), self.gt.data_ptr(), tuple(self.img.shape), tuple(self.gt.shape),
@@ -107,19 +153,23 @@ class IspModel:
 
     def _graph_replay(self):
         key = self._graph_signature()
-        if self._graph is not None and key == self._graph_key:
-            g_loss, g_update = self._graph
+        graphs = self.__dict__.setdefault('_graphs', {})   # one captured step per buffer set (double-buffered feed)
+        if key in graphs:
+            g_loss, g_update, l_pix = graphs[key]
             g_loss.replay()
             if g_update is not None:                       # data parallel: the collective stays outside the graphs
                 self._allreduce_grads()
                 g_update.replay()
-            self.log_dict['loss'] = self.l_pix
+            self.l_pix = l_pix
+            self.log_dict['loss'] = l_pix
             return True
-        self._graph = None
-        stable, self._last_key = key == getattr(self, '_last_key', None), key
-        # capture only once the same buffers / shapes / learning rates have been seen twice in a row (a loop that
-        # feeds fresh device tensors every step would otherwise re-capture every step)
-        if not stable or self._eager_steps < 2 or not (self.netG.fuse and self.loss_type == 'l2') or \
+        seen = self.__dict__.setdefault('_seen_keys', {})
+        seen[key] = seen.get(key, 0) + 1
+        if len(seen) > 8:                                   # a loop that feeds fresh device tensors every step: stay eager
+            seen.clear(); graphs.clear()
+        # capture only once the same buffers / shapes / learning rates have been seen before (a loop that feeds fresh
+        # device tensors every step would otherwise re-capture every step)
+        if seen.get(key, 0) < 2 or self._eager_steps < 2 or not (self.netG.fuse and self.loss_type == 'l2') or \
                 self.netG.fused_mse_step_plan() is None:
             return False
         try:
@@ -136,12 +186,14 @@ class IspModel:
                 g_update = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g_update, pool=g_loss.pool()):
                     self.optimizer_G.step()
-            self._graph, self._graph_key = (g_loss, g_update), key
+            graphs[key] = (g_loss, g_update, self.l_pix)
+            self._graph = graphs                           # (kept for callers that drop the graphs before teardown)
             return self._graph_replay()                    # capturing does not execute: run the step now
         except Exception as e:                             # capture is an optimisation: fall back to eager launches
             import logging
             logging.getLogger('base').warning('CUDA-graph capture of the tuning step failed (%s); running eagerly', e)
             self.use_graph, self._graph = False, None
+            graphs.clear()
             torch.cuda.synchronize()
             return False
 
@@ -150,16 +202,14 @@ class IspModel:
         if l_pix is None:
             self._output = self.netG(self.img)
             l_pix = (ops.l1_loss if self.loss_type == 'l1' else ops.mse_loss)(self._output, self.gt)
-        self.optimizer_G.zero_grad()
+        self._flat_grad.zero_()                        # p.grad are views of it; backward accumulates in place
         l_pix.backward()
         self.l_pix = l_pix.detach()
         self.log_dict['loss'] = self.l_pix             # device scalar; `.item()` it when logging
 
     def _allreduce_grads(self):
         if D.is_dist():
-            ps = [p for p in self.netG.trainable_parameters if p.grad is not None]
-            for p, g in zip(ps, D.allreduce_mean_flat([p.grad for p in ps])):
-                p.grad.copy_(g)
+            D.allreduce_mean_(self._flat_grad)
 
     def _step_eager(self, count=True):
         if count:
