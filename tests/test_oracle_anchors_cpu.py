@@ -59,3 +59,26 @@ def test_malvar_reproduces_linear_ramps_and_constants():
     assert float((out - img)[:, :, 2:-2, 2:-2].abs().max()) <= 1e-6
     const = torch.full((1, 3, 16, 16), 0.4)
     assert float((O.demosaic_laplacian(O.mosaic_bgr(const), 1.0) - const).abs().max()) <= 1e-6
+
+
+def test_fastnlm_is_opencv_fast_nl_means():
+    """The wrapper's option name and parameters (`fastnlm`: block_size, search_block, decay_factor, tools_origin.py:762-804)
+    are OpenCV's.  The oracle's definition reproduces `cv2.fastNlMeansDenoising` on a 3-channel 8-bit image (patch distance
+    averaged jointly over the channels, weights exp(-d2/h^2)) to within OpenCV's own 8-bit output rounding and fixed-point
+    weight table: <= 1 code max, <= 0.3 code mean, for several (block, search, h).  The Lab-space
+    `fastNlMeansDenoisingColored` is a different operator (it denoises L and ab separately): measured 1-3.5 codes mean
+    away on the same inputs, recorded here so the distance is on file (oracle/SPEC.md)."""
+    cv2 = pytest.importorskip('cv2')
+    rng = np.random.RandomState(3)
+    H, W = 48, 56
+    yy, xx = np.mgrid[0:H, 0:W]
+    clean = np.stack([120 + 60 * np.sin(xx / 9.0), 100 + 50 * np.cos(yy / 7.0), 140 + 40 * np.sin((xx + yy) / 11.0)], -1)
+    u8 = np.clip(clean + rng.randn(H, W, 3) * 8, 0, 255).round().astype(np.uint8)
+    x = torch.from_numpy(u8.astype(np.float32)).permute(2, 0, 1)[None]
+    for b, s, h in ((3, 3, 10.0), (3, 7, 10.0), (5, 11, 20.0)):
+        ours = O.denoise_fastnlm(x, [b], [s], [h])[0].permute(1, 2, 0).numpy()
+        cvg = cv2.fastNlMeansDenoising(u8, None, h, b, s).astype(np.float32)
+        d = np.abs(ours - cvg)
+        assert d.max() <= 1.0 and d.mean() <= 0.3, (b, s, h, d.max(), d.mean())
+        lab = cv2.fastNlMeansDenoisingColored(u8, None, h, h, b, s).astype(np.float32)
+        assert 0.3 < np.abs(ours - lab).mean() < 6.0          # a different operator, by a known margin

@@ -150,3 +150,30 @@ def test_anchors_identity_at_default_logits():
     assert (PO.m_wbmanual(x, sg([-1.38] * 3)) - x).abs().max() < 6e-3
     assert (PO.m_wbquadratic(x, sg(PO.WBQ_INIT)) - x).abs().max() < 2e-3
     assert (PO.m_gtmmanual(x, sg([-1.099, 0, 1.099])) - x).abs().max() < 1e-3
+
+
+def test_darts_step_against_reference_model(golden):
+    """`PO.darts_step` (the restatement the GPU test of round 1 compared with) held to a run of the reference's own
+    `DartsModel.optimize_alphas / optimize_parameters` (oracle/gen_golden_darts.py), n_step = 3, pruning active."""
+    g = golden('darts_model')
+    n_al = 5
+    oG, oV = PO.Supernet(3, 0.2, 10), PO.Supernet(3, 0.2, 10)
+    with torch.no_grad():
+        for i, a in enumerate(oG.alphas):
+            a.copy_(T(g['alpha0_%d' % i]))
+    r = PO.darts_step(oG, oV, T(g['img']), T(g['gt']), T(g['vimg']), T(g['vgt']), lr_G=0.01, momentum_G=0.9, lr_meta=0.01)
+    assert abs(float(r['val_loss'].detach()) - float(g['it0_val_loss'])) <= 1e-6
+    for i in range(n_al):
+        close(r['alpha_grad'][i], g['it0_alpha_grad_%d' % i], 2e-6)
+    # the reference applies the Adam step on the alphas before optimize_parameters: repeat the plain pass there
+    with torch.no_grad():
+        for i, a in enumerate(oG.alphas):
+            a.copy_(T(g['it0_alpha_%d' % i]))
+    y, _ = oG.forward(T(g['img']))
+    loss = ((y - T(g['gt'])) ** 2).mean()
+    assert abs(float(loss.detach()) - float(g['it0_loss'])) <= 1e-6
+    nz = [p for p in oG.trainable if p.numel() > 0]
+    grads = torch.autograd.grad(loss, nz, allow_unused=True)
+    assert len(nz) == int(g['n_params'])
+    for i, gr in enumerate(grads):
+        close(torch.zeros_like(nz[i]) if gr is None else gr, g['it0_param_grad_%d' % i], 2e-6)

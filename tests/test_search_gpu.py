@@ -150,3 +150,33 @@ def test_proxy_finetune_reduces_proxy_error_and_search_continues():
     assert e1 < e0, (e0, e1)
     m.feed_data(batch()); m.optimize_alphas(); m.optimize_parameters()
     assert torch.isfinite(m.log_dict['loss'])
+
+
+def test_darts_model_matches_reference_run(golden):
+    """Two full search iterations (optimize_alphas + optimize_parameters) of `search.DartsModel`, n_step = 3 with two
+    candidates pruned, against the golden recorded from the reference's own `DartsModel` (oracle/gen_golden_darts.py):
+    validation loss, alpha gradients, alphas after Adam, training loss, parameter gradients and parameters after
+    SGD-momentum -- after BOTH iterations (the second one exercises the momentum buffer in the virtual step, :212-218)."""
+    from reconfigisp_b200.search import DartsModel
+    g = golden('darts_model')
+    T = torch.from_numpy
+    o = _opt(3)
+    m = DartsModel(o)
+    with torch.no_grad():
+        for i, a in enumerate(m.netG.alphas):
+            a.copy_(T(g['alpha0_%d' % i]).cuda())
+    m.feed_data((T(g['img']), T(g['gt']), T(g['vimg']), T(g['vgt'])))
+    for it in range(2):
+        m.optimize_alphas()
+        assert abs(float(m.val_loss) - float(g['it%d_val_loss' % it])) <= 2e-5, it
+        for i, a in enumerate(m.netG.alphas):
+            relclose(a.grad, T(g['it%d_alpha_grad_%d' % (it, i)]), rtol=5e-3, atol=2e-7)
+            relclose(a, T(g['it%d_alpha_%d' % (it, i)]), rtol=1e-3, atol=1e-5)
+        m.optimize_parameters()
+        assert m.netG.pruned_paths == list(g['it%d_pruned' % it]), it
+        assert abs(float(m.log_dict['loss'].detach()) - float(g['it%d_loss' % it])) <= 2e-5, it
+        nz = [p for p in m.netG.trainable_parameters if p.nelement() > 0]
+        assert len(nz) == int(g['n_params'])
+        for i, p in enumerate(nz):
+            relclose(p.grad, T(g['it%d_param_grad_%d' % (it, i)]), rtol=5e-3, atol=2e-7)
+            relclose(p, T(g['it%d_param_%d' % (it, i)]), rtol=1e-4, atol=1e-6)
