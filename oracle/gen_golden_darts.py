@@ -31,8 +31,8 @@ def ref_opt(which='SuperPruneFifteenDemosFourBayerTwo', model='darts'):
             'path': {'pretrain_model_G': None, 'strict_load': True}}
 
 
-def inputs():
-    g = torch.Generator().manual_seed(10)
+def inputs(seed=10):
+    g = torch.Generator().manual_seed(seed)
     N, H, W = 2, 16, 16
     img, vimg = torch.rand(N, 1, H, W, generator=g) * 0.8 + 0.1, torch.rand(N, 1, H, W, generator=g) * 0.8 + 0.1
     gt, vgt = torch.rand(N, 3, H, W, generator=g), torch.rand(N, 3, H, W, generator=g)
@@ -54,8 +54,28 @@ def main():
         return orig_define(opt)
     networks.define_G = define_G
     dm.networks.define_G = define_G
-    img, gt, vimg, vgt, alphas0 = inputs()
-    rec = {'img': img, 'gt': gt, 'vimg': vimg, 'vgt': vgt}
+    # x^gamma has an unbounded derivative at 0 and the clamps have kinks: a recorded run in which some intermediate pixel
+    # sits within 1e-4 of 0 cannot be reproduced to a tolerance by ANY other fp32 implementation (a 1e-6 difference in that
+    # pixel moves a parameter gradient by 10 %).  Pick the first seed whose intermediates stay clear of the singularity.
+    from oracle import pipeline_oracle as PO
+    for seed in range(10, 60):
+        img, gt, vimg, vgt, alphas0 = inputs(seed)
+        probe = PO.Supernet(N_STEP, 0.2, 10)
+        with torch.no_grad():
+            for a, v in zip(probe.alphas, alphas0):
+                a.copy_(v)
+        worst = 1.0
+        for x in (img, vimg):
+            for t in probe.forward(x)[1][1:]:
+                t = t.detach()
+                near0 = t[(t > -1e-4) & (t < 1e-4)]
+                if near0.numel():
+                    worst = 0.0
+        if worst > 0:
+            break
+    assert worst > 0, 'no well-conditioned seed found'
+    print('input seed', seed)
+    rec = {'img': img, 'gt': gt, 'vimg': vimg, 'vgt': vgt, 'input_seed': torch.tensor(seed)}
     for i, a in enumerate(alphas0):
         rec['alpha0_%d' % i] = a
     with RL.cpu_only():

@@ -53,7 +53,7 @@ def test_darts_step_matches_oracle():
             a.copy_(v.cuda())
     m.optimize_parameters()
     nz = [p for p in m.netG.trainable_parameters if p.nelement() > 0]
-    assert abs(float(m.log_dict['loss']) - float(ref['loss2'])) <= 1e-5
+    assert abs(float(m.log_dict['loss'].detach()) - float(ref['loss2'].detach())) <= 1e-5
     for p, r in zip(nz, ref['param_grad']):
         if r is None:
             continue
