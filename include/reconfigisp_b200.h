@@ -219,6 +219,13 @@ int risp_mixed_bwd(const float* x, const float* dy, float* dx, float* dw, float*
                    const float* params, int param_stride, int P, const float* const* ext, int K_ext,
                    const float* w, void* workspace, size_t workspace_bytes, risp_stream_t stream);
 
+/* Same, and the upstream gradients of the materialised candidates leave the same pass: dext is a HOST array of K_ext DEVICE
+ * pointers (entries may be NULL); dext[i] receives w[K_cls+i] * dy (N,3,HW).  Saves one 24 B/px kernel per CNN candidate. */
+int risp_mixed_bwd_dext(const float* x, const float* dy, float* dx, float* dw, float* dparams, float* const* dext, int N,
+                        long long HW, const int* cls_ops, const int* cls_off, const int* cls_iarg, int K_cls,
+                        const float* params, int param_stride, int P, const float* const* ext, int K_ext,
+                        const float* w, void* workspace, size_t workspace_bytes, risp_stream_t stream);
+
 /* Single-plane (Bayer-domain) mixed-op: n_skip Skip candidates + K_ext materialised candidates
  * (the Bayer step: PathRestore14lBayer + Skip, super_prune...:57-74). */
 int risp_mixed1_fwd(const float* x, float* y, int N, long long HW, int n_skip, const float* const* ext,

@@ -127,5 +127,10 @@ def parr(tensors):
     return (ctypes.c_void_p * max(1, len(tensors)))(*[t.data_ptr() for t in tensors])
 
 
+def parr_opt(tensors):
+    """Host array of device pointers; None entries become NULL."""
+    return (ctypes.c_void_p * max(1, len(tensors)))(*[None if t is None else t.data_ptr() for t in tensors])
+
+
 def workspace(nbytes, device):
     return torch.empty(max(1, (nbytes + 3) // 4), dtype=torch.float32, device=device)

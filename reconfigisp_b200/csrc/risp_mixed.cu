@@ -25,6 +25,7 @@ struct MixDesc {
   int off[RISP_MAX_STAGES];
   int iarg[RISP_MAX_STAGES];
   const float* ext[RISP_MAX_BRANCHES];
+  float* dext[RISP_MAX_BRANCHES];     // backward: where w_e * dy goes (the upstream gradient of candidate e), or null
 };
 
 template <int VEC> struct V3;
@@ -57,6 +58,22 @@ template <> struct V3<1> {
 };
 
 template <int VEC> struct MixNpx { static constexpr int value = (VEC == 4) ? 4 : 2; };
+
+// 128-bit streaming load under a predicate (zeros when off): no branch, so the loads of a whole batch of candidate
+// outputs are in flight together instead of one dependent round trip per candidate
+__device__ __forceinline__ float4 ld_stream4_if(const float* p, bool on) {
+  float4 v;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %5, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
+               "mov.f32 %2, 0f00000000;\n\tmov.f32 %3, 0f00000000;\n\t"
+               "@q ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "r"((int)on));
+  return v;
+}
+constexpr int kExtBatch = 3;     // materialised candidates loaded together (3 planes x 128 bit each = 36 registers)
+#ifndef RISP_MIX_FWD_BATCH
+#define RISP_MIX_FWD_BATCH 4
+#endif
+constexpr int kExtBatchFwd = RISP_MIX_FWD_BATCH;  // measured: 1 CTA/SM with 4 candidates in flight beats 2 CTAs with 2 (0.58 vs 0.44 of HBM peak)
 
 // load / store one pixel group of a C-plane image (C = 1 or 3; missing planes read as 0)
 template <int VEC>
@@ -98,17 +115,22 @@ __device__ __forceinline__ void mix_store(const Px<MixNpx<VEC>::value>& px, floa
   }
 }
 
+#ifndef RISP_MIX_FWD_MINB
+#define RISP_MIX_FWD_MINB 1
+#endif
 template <int VEC>
-__global__ void __launch_bounds__(kT, 2)
+__global__ void __launch_bounds__(kT, RISP_MIX_FWD_MINB)
 mixed_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long HW, int C, MixDesc d,
                  const float* __restrict__ params, int pstride, const float* __restrict__ w) {
   constexpr int NPX = MixNpx<VEC>::value;
   const int n = blockIdx.y;
   const float* __restrict__ prow = params + (long long)n * pstride;
   const long long img = (long long)n * C * HW;
-  float wk[RISP_MAX_BRANCHES];
+  float wk[RISP_MAX_STAGES], wext[RISP_MAX_BRANCHES];
 #pragma unroll
-  for (int k = 0; k < RISP_MAX_BRANCHES; ++k) wk[k] = (k < d.K_cls + d.K_ext) ? w[k] : 0.f;
+  for (int k = 0; k < RISP_MAX_STAGES; ++k) wk[k] = (k < d.K_cls) ? w[k] : 0.f;
+#pragma unroll
+  for (int k = 0; k < RISP_MAX_BRANCHES; ++k) wext[k] = (k < d.K_ext) ? w[d.K_cls + k] : 0.f;
   const long long nvec = (VEC == 4) ? HW / 4 : (HW + 1) / 2;
   for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < nvec; i += (long long)gridDim.x * kT) {
     Px<NPX> X, Y;
@@ -126,16 +148,41 @@ mixed_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long H
         }
       }
     }
+    if (VEC == 4) {
 #pragma unroll
-    for (int e = 0; e < RISP_MAX_BRANCHES; ++e) {
-      if (e < d.K_ext) {
-        const float we = wk[d.K_cls + e];
-        if (!(we < 1e-9f)) {
-          Px<NPX> E;
-          mix_load<VEC>(E, d.ext[e] + img, HW, i, C);
+      for (int e0 = 0; e0 < RISP_MAX_BRANCHES; e0 += kExtBatchFwd) {
+        if (e0 < d.K_ext) {                                   // uniform
+          float4 E[kExtBatchFwd][3];
 #pragma unroll
-          for (int k = 0; k < NPX; ++k) {
-            Y.b[k] = fmaf(we, E.b[k], Y.b[k]); Y.g[k] = fmaf(we, E.g[k], Y.g[k]); Y.r[k] = fmaf(we, E.r[k], Y.r[k]);
+          for (int u = 0; u < kExtBatchFwd; ++u) {
+            const int e = e0 + u;
+            const bool live = (e < RISP_MAX_BRANCHES) && (e < d.K_ext) && !(wext[e < RISP_MAX_BRANCHES ? e : 0] < 1e-9f);
+            const float* p = d.ext[e < RISP_MAX_BRANCHES ? e : 0] + img + 4 * i;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) E[u][c] = ld_stream4_if(p + c * HW, live && c < C);
+          }
+#pragma unroll
+          for (int u = 0; u < kExtBatchFwd; ++u) {
+            const int e = e0 + u;
+            const float we = (e < RISP_MAX_BRANCHES && e < d.K_ext && !(wext[e < RISP_MAX_BRANCHES ? e : 0] < 1e-9f)) ? wext[e < RISP_MAX_BRANCHES ? e : 0] : 0.f;
+            Y.b[0] = fmaf(we, E[u][0].x, Y.b[0]); Y.b[1] = fmaf(we, E[u][0].y, Y.b[1]); Y.b[2] = fmaf(we, E[u][0].z, Y.b[2]); Y.b[3] = fmaf(we, E[u][0].w, Y.b[3]);
+            Y.g[0] = fmaf(we, E[u][1].x, Y.g[0]); Y.g[1] = fmaf(we, E[u][1].y, Y.g[1]); Y.g[2] = fmaf(we, E[u][1].z, Y.g[2]); Y.g[3] = fmaf(we, E[u][1].w, Y.g[3]);
+            Y.r[0] = fmaf(we, E[u][2].x, Y.r[0]); Y.r[1] = fmaf(we, E[u][2].y, Y.r[1]); Y.r[2] = fmaf(we, E[u][2].z, Y.r[2]); Y.r[3] = fmaf(we, E[u][2].w, Y.r[3]);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < RISP_MAX_BRANCHES; ++e) {
+        if (e < d.K_ext) {
+          const float we = wext[e];
+          if (!(we < 1e-9f)) {
+            Px<NPX> E;
+            mix_load<VEC>(E, d.ext[e] + img, HW, i, C);
+#pragma unroll
+            for (int k = 0; k < NPX; ++k) {
+              Y.b[k] = fmaf(we, E.b[k], Y.b[k]); Y.g[k] = fmaf(we, E.g[k], Y.g[k]); Y.r[k] = fmaf(we, E.r[k], Y.r[k]);
+            }
           }
         }
       }
@@ -153,9 +200,13 @@ mixed_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, floa
   const int n = blockIdx.y;
   const float* __restrict__ prow = params + (long long)n * pstride;
   const long long img = (long long)n * C * HW;
-  float wk[RISP_MAX_BRANCHES], dot[RISP_MAX_BRANCHES];
+  // classical branches j (static index) and materialised branches e (static index) keep separate weights / dot products;
+  // the branch number K_cls + e only appears when the partial row is written
+  float wk[RISP_MAX_STAGES], dot[RISP_MAX_STAGES], wext[RISP_MAX_BRANCHES], dote[RISP_MAX_BRANCHES];
 #pragma unroll
-  for (int k = 0; k < RISP_MAX_BRANCHES; ++k) { wk[k] = (k < d.K_cls + d.K_ext) ? w[k] : 0.f; dot[k] = 0.f; }
+  for (int k = 0; k < RISP_MAX_STAGES; ++k) { wk[k] = (k < d.K_cls) ? w[k] : 0.f; dot[k] = 0.f; }
+#pragma unroll
+  for (int k = 0; k < RISP_MAX_BRANCHES; ++k) { wext[k] = (k < d.K_ext) ? w[d.K_cls + k] : 0.f; dote[k] = 0.f; }
   float accS[RISP_MAX_STAGES][RISP_SMALL_ACC];
   float2 accB[RISP_BIG_ACC];
 #pragma unroll
@@ -189,18 +240,56 @@ mixed_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, floa
         }
       }
     }
+    if (VEC == 4) {
 #pragma unroll
-    for (int e = 0; e < RISP_MAX_BRANCHES; ++e) {
-      if (e < d.K_ext && !(wk[d.K_cls + e] < 1e-9f)) {
-        Px<NPX> E;
-        mix_load<VEC>(E, d.ext[e] + img, HW, i, C);
-        float a = 0.f;
+      for (int e0 = 0; e0 < RISP_MAX_BRANCHES; e0 += kExtBatch) {
+        if (e0 < d.K_ext) {                                   // uniform
+          float4 E[kExtBatch][3];
 #pragma unroll
-        for (int k = 0; k < NPX; ++k) a = fmaf(G.b[k], E.b[k], fmaf(G.g[k], E.g[k], fmaf(G.r[k], E.r[k], a)));
-        // dot[] is indexed with a runtime value only through this unrolled select
+          for (int u = 0; u < kExtBatch; ++u) {
+            const int e = (e0 + u < RISP_MAX_BRANCHES) ? e0 + u : 0;
+            const bool live = (e0 + u < RISP_MAX_BRANCHES) && (e < d.K_ext) && !(wext[e] < 1e-9f);
+            const float* p = d.ext[e] + img + 4 * i;
 #pragma unroll
-        for (int q = 0; q < RISP_MAX_BRANCHES; ++q)
-          if (q == d.K_cls + e) dot[q] += a;
+            for (int c = 0; c < 3; ++c) E[u][c] = ld_stream4_if(p + c * HW, live && c < C);
+          }
+#pragma unroll
+          for (int u = 0; u < kExtBatch; ++u) {
+            if (e0 + u < RISP_MAX_BRANCHES) {
+              float a = 0.f;
+              a = fmaf(G.b[0], E[u][0].x, fmaf(G.b[1], E[u][0].y, fmaf(G.b[2], E[u][0].z, fmaf(G.b[3], E[u][0].w, a))));
+              a = fmaf(G.g[0], E[u][1].x, fmaf(G.g[1], E[u][1].y, fmaf(G.g[2], E[u][1].z, fmaf(G.g[3], E[u][1].w, a))));
+              a = fmaf(G.r[0], E[u][2].x, fmaf(G.r[1], E[u][2].y, fmaf(G.r[2], E[u][2].z, fmaf(G.r[3], E[u][2].w, a))));
+              dote[e0 + u] += a;                               // skipped branches loaded zeros
+              float* de = d.dext[e0 + u];
+              if (de != nullptr && e0 + u < d.K_ext) {         // uniform: d ext_e = w_e * dy, written from the registers
+                const float we = wext[e0 + u];
+                float* q = de + img + 4 * i;
+                st_stream4(q, make_float4(we * G.b[0], we * G.b[1], we * G.b[2], we * G.b[3]));
+                if (C > 1) st_stream4(q + HW, make_float4(we * G.g[0], we * G.g[1], we * G.g[2], we * G.g[3]));
+                if (C > 2) st_stream4(q + 2 * HW, make_float4(we * G.r[0], we * G.r[1], we * G.r[2], we * G.r[3]));
+              }
+            }
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < RISP_MAX_BRANCHES; ++e) {
+        if (e < d.K_ext && !(wext[e] < 1e-9f)) {
+          Px<NPX> E;
+          mix_load<VEC>(E, d.ext[e] + img, HW, i, C);
+          float a = 0.f;
+#pragma unroll
+          for (int k = 0; k < NPX; ++k) a = fmaf(G.b[k], E.b[k], fmaf(G.g[k], E.g[k], fmaf(G.r[k], E.r[k], a)));
+          dote[e] += a;
+        }
+        if (e < d.K_ext && d.dext[e] != nullptr) {
+          Px<NPX> DE;
+#pragma unroll
+          for (int k = 0; k < NPX; ++k) { DE.b[k] = wext[e] * G.b[k]; DE.g[k] = wext[e] * G.g[k]; DE.r[k] = wext[e] * G.r[k]; }
+          mix_store<VEC>(DE, d.dext[e] + img, HW, i, C);
+        }
       }
     }
     if (dx) mix_store<VEC>(DX, dx + img, HW, i, C);
@@ -230,10 +319,20 @@ mixed_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, floa
     float v0 = BIG ? warp_sum(accB[k].x * bigw) : 0.f, v1 = BIG ? warp_sum(accB[k].y * bigw) : 0.f;
     if (lane == 0) { red[wid][RISP_SLOT_BIG + 2 * k] = v0; red[wid][RISP_SLOT_BIG + 2 * k + 1] = v1; }
   }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < RISP_MAX_BRANCHES; ++k) red[wid][RISP_NSLOT + k] = 0.f;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < RISP_MAX_STAGES; ++k) {
+    float v = warp_sum(dot[k]);
+    if (lane == 0 && k < d.K_cls) red[wid][RISP_NSLOT + k] = v;
+  }
 #pragma unroll
   for (int k = 0; k < RISP_MAX_BRANCHES; ++k) {
-    float v = warp_sum(dot[k]);
-    if (lane == 0) red[wid][RISP_NSLOT + k] = v;
+    float v = warp_sum(dote[k]);
+    if (lane == 0 && k < d.K_ext) red[wid][RISP_NSLOT + d.K_cls + k] = v;
   }
   if (lane == 0) { red[wid][RISP_SLOT_LOSS] = 0.f; red[wid][RISP_SLOT_LOSS + 1] = 0.f; }
   __syncthreads();
@@ -419,7 +518,7 @@ static int mixed_fwd_impl(const float* x, float* y, int N, long long HW, int C, 
 static int mixed_bwd_impl(const float* x, const float* dy, float* dx, float* dw, float* dparams, int N, long long HW,
                           int C, const int* cls_ops, const int* cls_off, const int* cls_iarg, int K_cls,
                           const float* params, int param_stride, int P, const float* const* ext, int K_ext,
-                          const float* w, void* workspace, size_t workspace_bytes, risp_stream_t stream) {
+                          const float* w, void* workspace, size_t workspace_bytes, risp_stream_t stream, float* const* dext = nullptr) {
   int rc = mixed_common_checks("risp_mixed_bwd", x, N, HW, C);
   if (rc != RISP_OK) return rc;
   RISP_REQUIRE(dy && dw && w, RISP_E_INVALID, "risp_mixed_bwd: null dy / dw / w");
@@ -438,7 +537,11 @@ static int mixed_bwd_impl(const float* x, const float* dy, float* dx, float* dw,
   size_t need = risp_mixed_bwd_workspace(N, HW, P, K);
   RISP_REQUIRE(workspace && workspace_bytes >= need, RISP_E_WORKSPACE, "risp_mixed_bwd: workspace %zu < %zu", workspace_bytes, need);
   bool vec = (HW % 4 == 0) && aligned16(x) && aligned16(dy) && (!dx || aligned16(dx));
-  for (int e = 0; e < K_ext; ++e) vec = vec && aligned16(ext[e]);
+  for (int e = 0; e < K_ext; ++e) {
+    vec = vec && aligned16(ext[e]);
+    d.dext[e] = dext ? dext[e] : nullptr;
+    vec = vec && (!d.dext[e] || aligned16(d.dext[e]));
+  }
   const int B = mix_blocks(N, HW);
   dim3 grid(B, N);
   cudaStream_t st = as_stream(stream);
@@ -486,6 +589,14 @@ extern "C" int risp_mixed_bwd(const float* x, const float* dy, float* dx, float*
                               const float* w, void* workspace, size_t workspace_bytes, risp_stream_t stream) {
   return mixed_bwd_impl(x, dy, dx, dw, dparams, N, HW, 3, cls_ops, cls_off, cls_iarg, K_cls, params, param_stride, P,
                         ext, K_ext, w, workspace, workspace_bytes, stream);
+}
+
+extern "C" int risp_mixed_bwd_dext(const float* x, const float* dy, float* dx, float* dw, float* dparams, float* const* dext,
+                                   int N, long long HW, const int* cls_ops, const int* cls_off, const int* cls_iarg, int K_cls,
+                                   const float* params, int param_stride, int P, const float* const* ext, int K_ext,
+                                   const float* w, void* workspace, size_t workspace_bytes, risp_stream_t stream) {
+  return mixed_bwd_impl(x, dy, dx, dw, dparams, N, HW, 3, cls_ops, cls_off, cls_iarg, K_cls, params, param_stride, P,
+                        ext, K_ext, w, workspace, workspace_bytes, stream, dext);
 }
 
 // single-plane (Bayer-domain) variants: candidates are Skip and materialised tensors

@@ -214,8 +214,8 @@ def mixed_op_probe(timed, N, H, W, hbm_peak_gbs, K_ext=9):
     """Time the fused mixed-op of ONE sRGB step in isolation at a size where the HBM roofline means something
     (bench.py --workload search): the 6 classical candidates are evaluated in registers from one read of x, the K_ext = 9
     CNN candidates are materialised inputs.  Algorithmic bytes: forward 12 (x) + 12*K_ext + 12 (y) = 132 B/px,
-    backward 12 (dy) + 12 (x) + 12*K_ext (dot products with the CNN outputs) + 12 (dx) = 144 B/px here (the upstream
-    gradients of the CNN candidates, w_i*dy, are fused into their consumers: `scale_by_device`, not written by this kernel)."""
+    backward 12 (dy) + 12 (x) + 12*K_ext (dot products with the CNN outputs) + 12 (dx) + 12*K_ext (the upstream gradients
+    w_i*dy of the CNN candidates, written by the same kernel) = 252 B/px."""
     dev = torch.device('cuda')
     chain = ops.Chain([op for _, op in SRGB_CLASSICAL])
     x = torch.rand(N, 3, H, W, device=dev).requires_grad_()
@@ -229,8 +229,8 @@ def mixed_op_probe(timed, N, H, W, hbm_peak_gbs, K_ext=9):
     with torch.no_grad():
         ms_f = timed(lambda: ops.mixed_op(x, chain, table, w, ext), 5, 2) / 5
     y = ops.mixed_op(x, chain, table, w, ext)
-    ms_b = timed(lambda: torch.autograd.grad(y, (x, table, w), dy, retain_graph=True), 5, 2) / 5
-    bf, bb = 12 + 12 * K_ext + 12, 12 + 12 + 12 * K_ext + 12
+    ms_b = timed(lambda: torch.autograd.grad(y, [x, table, w] + ext, dy, retain_graph=True), 5, 2) / 5
+    bf, bb = 12 + 12 * K_ext + 12, 12 + 12 + 12 * K_ext + 12 + 12 * K_ext
     return {'shape': [N, 3, H, W], 'K_classical': len(SRGB_CLASSICAL), 'K_ext': K_ext,
             'fwd': {'ms': round(ms_f, 4), 'bytes_per_px': bf, 'GBps': round(bf * px / ms_f / 1e6, 1), 'frac': round(bf * px / ms_f / 1e6 / hbm_peak_gbs, 4)},
             'bwd': {'ms': round(ms_b, 4), 'bytes_per_px': bb, 'GBps': round(bb * px / ms_b / 1e6, 1), 'frac': round(bb * px / ms_b / 1e6 / hbm_peak_gbs, 4)},

@@ -509,16 +509,20 @@ class _MixedFn(torch.autograd.Function):
         P = chain.P
         dpar = torch.empty((1 if ctx.stride == 0 else N, P), device=x.device, dtype=torch.float32) if P else None
         ws = L.workspace(L.size('risp_mixed_bwd_workspace', N, H * W, P, K), x.device)
+        dext = None
         if C == 3:
-            L.call('risp_mixed_bwd', L.ptr(x), L.ptr(dy), L.ptr(dx), L.ptr(dw), L.ptr(dpar), N, H * W, *chain.desc(),
-                   L.ptr(tab), ctx.stride, P, L.parr(ext), len(ext), L.ptr(w), L.ptr(ws), ws.numel() * 4, L.stream())
+            # d ext_i = w_i * dy leaves the same pass (written from the registers that hold dy)
+            dext = [torch.empty_like(dy) if ctx.needs_input_grad[5 + i] else None for i in range(len(ext))]
+            L.call('risp_mixed_bwd_dext', L.ptr(x), L.ptr(dy), L.ptr(dx), L.ptr(dw), L.ptr(dpar), L.parr_opt(dext), N, H * W,
+                   *chain.desc(), L.ptr(tab), ctx.stride, P, L.parr(ext), len(ext), L.ptr(w), L.ptr(ws), ws.numel() * 4, L.stream())
         else:
             L.call('risp_mixed1_bwd', L.ptr(x), L.ptr(dy), L.ptr(dx), L.ptr(dw), N, H * W, chain.S, L.parr(ext),
                    len(ext), L.ptr(w), L.ptr(ws), ws.numel() * 4, L.stream())
         if dpar is not None:
             dpar = dpar.view(ctx.pshape)
         # d ext_i = w_i * dy : a skipped branch (w < 1e-9) gets no gradient, like the reference's `continue`
-        dext = [scale_by_device(dy, w, chain.S + i) if ctx.needs_input_grad[5 + i] else None for i in range(len(ext))]
+        if dext is None:
+            dext = [scale_by_device(dy, w, chain.S + i) if ctx.needs_input_grad[5 + i] else None for i in range(len(ext))]
         return (dx, dpar, dw, None, None, *dext)
 
 
