@@ -5,6 +5,7 @@
 // planes in shared memory (coalesced row segments, border rule applied while loading), so every input
 // pixel is fetched from L2/HBM ~once and the window loops run out of shared memory.
 #include "risp_common.cuh"
+#include "risp_march.cuh"
 
 namespace risp {
 
@@ -20,17 +21,21 @@ __device__ __forceinline__ int border_idx(int i, int n, int mode) {
   return i;
 }
 
-// loads planes [0,C) of image n: tile origin (y0-R, x0-R), (TH+2R) x (TW+2R) floats per plane
+// loads planes [0,C) of image n: tile origin (y0-R, x0-R), (TH+2R) x (TW+2R) floats per plane.  A warp takes whole tile
+// rows (lanes = consecutive columns: coalesced row segments, border rule per element, no division in the loop).
 template <int C>
 __device__ __forceinline__ void load_tile(float* sh, const float* __restrict__ img, int H, int W, int y0, int x0, int R,
                                           int mode, float scale) {
   const int tw = TW + 2 * R, th = TH + 2 * R;
   const long long plane = (long long)H * W;
-  for (int i = threadIdx.x; i < tw * th; i += kT) {
-    const int ly = i / tw, lx = i % tw;
-    const int gy = border_idx(y0 - R + ly, H, mode), gx = border_idx(x0 - R + lx, W, mode);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int ly = wid; ly < th; ly += kT / 32) {
+    const long long ro = (long long)border_idx(y0 - R + ly, H, mode) * W;
+    for (int lx = lane; lx < tw; lx += 32) {
+      const int gx = border_idx(x0 - R + lx, W, mode);
 #pragma unroll
-    for (int c = 0; c < C; ++c) sh[c * tw * th + i] = __ldg(img + c * plane + (long long)gy * W + gx) * scale;
+      for (int c = 0; c < C; ++c) sh[c * tw * th + ly * tw + lx] = __ldg(img + c * plane + ro + gx) * scale;
+    }
   }
 }
 
@@ -128,6 +133,45 @@ __device__ __forceinline__ float median9(float* v) {
   return v[4];
 }
 
+// Exact median of K*K window elements by forgetful selection: keep t = n/2 + 2 candidates in registers; the minimum and the
+// maximum of any t elements cannot be the median, so each round drops both and takes in one unseen element; 3 remain at the
+// end.  ~0.75 t^2 compare-exchanges (K = 5: 147, 7: 507, 9: 1323) instead of 32 counting passes over the window.
+template <int CUR, int T>
+__device__ __forceinline__ void minmax_to_ends(float (&a)[T]) {      // a[0] <- min, a[CUR-1] <- max of a[0..CUR)
+#pragma unroll
+  for (int i = 0; i < CUR / 2; ++i) cswap(a[i], a[CUR - 1 - i]);
+#pragma unroll
+  for (int i = 1; i < (CUR + 1) / 2; ++i) cswap(a[0], a[i]);
+#pragma unroll
+  for (int i = CUR / 2; i < CUR - 1; ++i) cswap(a[i], a[CUR - 1]);
+}
+template <int K, int CUR, int NEXT, int T>
+struct Forget {
+  static __device__ __forceinline__ float run(float (&a)[T], const float* __restrict__ c0, int tw) {
+    minmax_to_ends<CUR, T>(a);
+    if constexpr (CUR == 3) {
+      return a[1];
+    } else {
+      constexpr int n = K * K, R = K / 2;
+      if constexpr (NEXT < n) {           // the minimum's slot takes the next unseen element; the maximum (last) is dropped
+        a[0] = c0[(NEXT / K - R) * tw + (NEXT % K - R)];
+        return Forget<K, CUR - 1, NEXT + 1, T>::run(a, c0, tw);
+      } else {                            // nothing unseen: drop both ends (move the last kept element into slot 0)
+        a[0] = a[CUR - 2];
+        return Forget<K, CUR - 2, NEXT, T>::run(a, c0, tw);
+      }
+    }
+  }
+};
+template <int K>
+__device__ __forceinline__ float median_select(const float* __restrict__ c0, int tw) {
+  constexpr int n = K * K, T = n / 2 + 2, R = K / 2;
+  float a[T];
+#pragma unroll
+  for (int i = 0; i < T; ++i) a[i] = c0[(i / K - R) * tw + (i % K - R)];
+  return Forget<K, T, T, T>::run(a, c0, tw);
+}
+
 __device__ __forceinline__ unsigned int okey(float f) {
   unsigned int b = __float_as_uint(f);
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
@@ -157,6 +201,12 @@ median_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, 
 #pragma unroll
       for (int dx = -1; dx <= 1; ++dx) v[(dy + 1) * 3 + dx + 1] = c0[dy * tw + dx];
     out = median9(v);
+  } else if (R == 2) {
+    out = median_select<5>(c0, tw);
+  } else if (R == 3) {
+    out = median_select<7>(c0, tw);
+  } else if (R == 4) {
+    out = median_select<9>(c0, tw);
   } else {
     // exact selection by bit-wise binary search on order-preserving keys: find the largest key K such
     // that #(elements >= K) >= rank_from_top, i.e. the median element itself
@@ -175,7 +225,9 @@ median_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, 
   y[(long long)blockIdx.z * plane + (long long)gy * W + gx] = out;
 }
 
-// ---- guided filter (self-guided), two passes --------------------------------------------------------------
+// ---- guided filter (self-guided), two passes, separable box sums ------------------------------------------------
+// Each pass stages the tile + halo, forms the horizontal window sums of every staged row once (2R+1 adds per element
+// instead of (2R+1)^2 per output), then every thread adds 2R+1 of them vertically.
 __global__ void __launch_bounds__(kT)
 guided_ab_kernel(const float* __restrict__ x, float* __restrict__ a_out, float* __restrict__ b_out, int H, int W, int R,
                  float eps) {
@@ -183,16 +235,24 @@ guided_ab_kernel(const float* __restrict__ x, float* __restrict__ a_out, float* 
   const long long plane = (long long)H * W;
   const float* img = x + (long long)blockIdx.z * plane;
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  const int tw = TW + 2 * R, th = TH + 2 * R;
+  float* hs = sh + tw * th;            // [th][TW] horizontal sums of x
+  float* hs2 = hs + th * TW;           // ... of x^2
   load_tile<1>(sh, img, H, W, y0, x0, R, BORDER_REFLECT101, 1.f);
+  __syncthreads();
+  for (int i = threadIdx.x; i < th * TW; i += kT) {
+    const int ly = i / TW, lx = i % TW;
+    const float* row = sh + ly * tw + lx;
+    float s = 0.f, s2 = 0.f;
+    for (int dx = 0; dx <= 2 * R; ++dx) { const float v = row[dx]; s += v; s2 = fmaf(v, v, s2); }
+    hs[i] = s; hs2[i] = s2;
+  }
   __syncthreads();
   const int tx = threadIdx.x % TW, ty = threadIdx.x / TW;
   const int gx = x0 + tx, gy = y0 + ty;
   if (gx >= W || gy >= H) return;
-  const int tw = TW + 2 * R;
-  const float* c0 = sh + (ty + R) * tw + tx + R;
   float s = 0.f, s2 = 0.f;
-  for (int dy = -R; dy <= R; ++dy)
-    for (int dx = -R; dx <= R; ++dx) { float v = c0[dy * tw + dx]; s += v; s2 = fmaf(v, v, s2); }
+  for (int dy = 0; dy <= 2 * R; ++dy) { s += hs[(ty + dy) * TW + tx]; s2 += hs2[(ty + dy) * TW + tx]; }
   const float inv = 1.f / (float)((2 * R + 1) * (2 * R + 1));
   const float mean = s * inv, var = s2 * inv - mean * mean;
   const float a = var / (var + eps);
@@ -207,17 +267,25 @@ guided_out_kernel(const float* __restrict__ x, const float* __restrict__ a_in, c
   const long long plane = (long long)H * W;
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
   const int tw = TW + 2 * R, th = TH + 2 * R;
+  float* hsa = sh + 2 * tw * th;
+  float* hsb = hsa + th * TW;
   load_tile<1>(sh, a_in + (long long)blockIdx.z * plane, H, W, y0, x0, R, BORDER_REFLECT101, 1.f);
   load_tile<1>(sh + tw * th, b_in + (long long)blockIdx.z * plane, H, W, y0, x0, R, BORDER_REFLECT101, 1.f);
+  __syncthreads();
+  for (int i = threadIdx.x; i < th * TW; i += kT) {
+    const int ly = i / TW, lx = i % TW;
+    const float* ra = sh + ly * tw + lx;
+    const float* rb = ra + tw * th;
+    float sa = 0.f, sb = 0.f;
+    for (int dx = 0; dx <= 2 * R; ++dx) { sa += ra[dx]; sb += rb[dx]; }
+    hsa[i] = sa; hsb[i] = sb;
+  }
   __syncthreads();
   const int tx = threadIdx.x % TW, ty = threadIdx.x / TW;
   const int gx = x0 + tx, gy = y0 + ty;
   if (gx >= W || gy >= H) return;
-  const float* ca = sh + (ty + R) * tw + tx + R;
-  const float* cb = ca + tw * th;
   float sa = 0.f, sb = 0.f;
-  for (int dy = -R; dy <= R; ++dy)
-    for (int dx = -R; dx <= R; ++dx) { sa += ca[dy * tw + dx]; sb += cb[dy * tw + dx]; }
+  for (int dy = 0; dy <= 2 * R; ++dy) { sa += hsa[(ty + dy) * TW + tx]; sb += hsb[(ty + dy) * TW + tx]; }
   const float inv = 1.f / (float)((2 * R + 1) * (2 * R + 1));
   const long long o = (long long)blockIdx.z * plane + (long long)gy * W + gx;
   y[o] = sa * inv * x[o] + sb * inv;
@@ -329,6 +397,71 @@ sharpen_bwd_dx_kernel(const float* __restrict__ e, float* __restrict__ dx, int H
   dx[o] = fmaf(1.f + a, ep[(long long)gy * W + gx], -a * bt);
 }
 
+// ---- register-marching fast paths (risp_march.cuh) -----------------------------------------------------------
+struct Median3F {
+  __device__ __forceinline__ void operator()(const float (&w)[1][3][6], float (&o)[1][4], int) const {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v[9];
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) v[j * 3 + i] = w[0][j][k + i];
+      o[0][k] = median9(v);
+    }
+  }
+};
+struct SharpenF {
+  const float* amount;
+  __device__ __forceinline__ void operator()(const float (&w)[1][5][8], float (&o)[1][4], int zp) const {
+    const float a = __ldg(amount + zp / 3);
+    const float kb[5] = {1.f / 16, 4.f / 16, 6.f / 16, 4.f / 16, 1.f / 16};
+    float col[8];                                   // vertical pass once per window column, shared by the 4 pixels
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float c = 0.f;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) c = fmaf(kb[j], w[0][j][i], c);
+      col[i] = c;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float b = 0.f;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) b = fmaf(kb[i], col[k + i], b);
+      const float v = w[0][2][k + 2];
+      o[0][k] = sat01(fmaf(a, v - b, v));
+    }
+  }
+};
+// window 3 (the only size the reference wrapper can produce for p in [0,1): tools_origin.py:698) or 1, per image
+struct Bilateral3F {
+  const int* window; const float* sigma_color; const float* sigma_space;
+  __device__ __forceinline__ void operator()(const float (&w)[3][3][6], float (&o)[3][4], int n) const {
+    const int R = __ldg(window + n) / 2;
+    const float sc = __ldg(sigma_color + n), ss = __ldg(sigma_space + n);
+    const float kc = -0.5f / (sc * sc), ks = -0.5f / (ss * ss);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float cb = w[0][1][k + 1], cg = w[1][1][k + 1], cr = w[2][1][k + 1];
+      float nb = cb, ng = cg, nr = cr, den = 1.f;                 // centre tap: weight exp(0)
+      if (R >= 1) {                                             // circular support r^2 <= R^2: the 4-neighbour cross
+        const int dys[4] = {-1, 1, 0, 0}, dxs[4] = {0, 0, -1, 1};
+        const float ws1 = __expf(ks);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float vb = w[0][1 + dys[t]][k + 1 + dxs[t]], vg = w[1][1 + dys[t]][k + 1 + dxs[t]], vr = w[2][1 + dys[t]][k + 1 + dxs[t]];
+          const float dist = fabsf(vb - cb) + fabsf(vg - cg) + fabsf(vr - cr);
+          const float wgt = __expf(dist * dist * kc) * ws1;
+          nb = fmaf(wgt, vb, nb); ng = fmaf(wgt, vg, ng); nr = fmaf(wgt, vr, nr); den += wgt;
+        }
+      }
+      const float inv = 1.f / den;
+      o[0][k] = nb * inv; o[1][k] = ng * inv; o[2][k] = nr * inv;
+    }
+  }
+};
+
 static dim3 tile_grid(int H, int W, int Z) { return dim3((unsigned)cdiv(W, TW), (unsigned)cdiv(H, TH), (unsigned)Z); }
 static size_t tile_smem(int R, int planes) { return sizeof(float) * (size_t)planes * (TW + 2 * R) * (TH + 2 * R); }
 
@@ -345,6 +478,12 @@ extern "C" int risp_bilateral_fwd(const float* x, float* y, int N, int H, int W,
                "risp_bilateral_fwd: max_window %d must be odd and <= %d", max_window, 2 * kMaxR + 1);
   RISP_REQUIRE(N <= 65535, RISP_E_INVALID, "risp_bilateral_fwd: batch too large");
   const int R = max_window / 2;
+  if (R <= 1 && march::usable(x, y, H, W, 1)) {
+    const march::Geom g = march::geometry(H, W, N);
+    march::march_kernel<1, 3, march::REFLECT101, Bilateral3F><<<g.grid, march::kWarps * 32, 0, as_stream(stream)>>>(
+        x, y, H, W, g.rows_per_chunk, Bilateral3F{window, sigma_color, sigma_space});
+    return check_launch("march_kernel<bilateral3>");
+  }
   bilateral_kernel<<<tile_grid(H, W, N), kT, tile_smem(R, 3), as_stream(stream)>>>(x, y, H, W, window, sigma_color,
                                                                                 sigma_space, R);
   return check_launch("bilateral_kernel");
@@ -368,6 +507,12 @@ extern "C" int risp_median_fwd(const float* x, float* y, int N, int H, int W, in
                "risp_median_fwd: size %d must be odd and in [3,%d]", size, 2 * kMaxR + 1);
   RISP_REQUIRE((long long)N * 3 <= 65535, RISP_E_INVALID, "risp_median_fwd: batch too large");
   const int R = size / 2;
+  if (R == 1 && march::usable(x, y, H, W, 1)) {
+    const march::Geom g = march::geometry(H, W, N * 3);
+    march::march_kernel<1, 1, march::REPLICATE, Median3F><<<g.grid, march::kWarps * 32, 0, as_stream(stream)>>>(
+        x, y, H, W, g.rows_per_chunk, Median3F{});
+    return check_launch("march_kernel<median3>");
+  }
   median_kernel<<<tile_grid(H, W, N * 3), kT, tile_smem(R, 1), as_stream(stream)>>>(x, y, H, W, R);
   return check_launch("median_kernel");
 }
@@ -386,8 +531,8 @@ extern "C" int risp_guided_fwd(const float* x, float* y, int N, int H, int W, in
   cudaStream_t st = as_stream(stream);
   float* a = static_cast<float*>(workspace);
   float* b = a + (size_t)N * 3 * H * W;
-  guided_ab_kernel<<<tile_grid(H, W, N * 3), kT, tile_smem(radius, 1), st>>>(x, a, b, H, W, radius, eps);
-  guided_out_kernel<<<tile_grid(H, W, N * 3), kT, tile_smem(radius, 2), st>>>(x, a, b, y, H, W, radius);
+  guided_ab_kernel<<<tile_grid(H, W, N * 3), kT, tile_smem(radius, 1) + 2 * sizeof(float) * (TH + 2 * radius) * TW, st>>>(x, a, b, H, W, radius, eps);
+  guided_out_kernel<<<tile_grid(H, W, N * 3), kT, tile_smem(radius, 2) + 2 * sizeof(float) * (TH + 2 * radius) * TW, st>>>(x, a, b, y, H, W, radius);
   return check_launch("guided kernels");
 }
 
@@ -395,6 +540,12 @@ extern "C" int risp_sharpen_fwd(const float* x, float* y, int N, int H, int W, c
                                 risp_stream_t stream) {
   RISP_REQUIRE(x && y && amount && N > 0 && H > 2 && W > 2, RISP_E_INVALID, "risp_sharpen_fwd: bad arguments");
   RISP_REQUIRE((long long)N * 3 <= 65535, RISP_E_INVALID, "risp_sharpen_fwd: batch too large");
+  if (march::usable(x, y, H, W, 2)) {
+    const march::Geom g = march::geometry(H, W, N * 3);
+    march::march_kernel<2, 1, march::REFLECT101, SharpenF><<<g.grid, march::kWarps * 32, 0, as_stream(stream)>>>(
+        x, y, H, W, g.rows_per_chunk, SharpenF{amount});
+    return check_launch("march_kernel<sharpen>");
+  }
   sharpen_fwd_kernel<<<tile_grid(H, W, N * 3), kT, tile_smem(2, 1), as_stream(stream)>>>(x, y, H, W, amount);
   return check_launch("sharpen_fwd_kernel");
 }

@@ -519,3 +519,24 @@ def test_conv2d_weight_and_bias_gradient(ops, cfg, path):
         errw = (gw.cpu().double() - gwo).abs()
         assert float(errw.max()) <= (20 if relu_out else 1) * tw, (cfg, path, relu_in, float(errw.max()), tw)
         assert maxabs(gb, gbo) <= (20 if relu_out else 1) * 2e-5 * max(1.0, float(gbo.abs().max())), (cfg, path, relu_in)
+
+
+@pytest.mark.parametrize('shape', [(2, 38, 136), (1, 5, 4), (1, 64, 520), (3, 9, 128)])
+def test_stencil_marching_fast_paths(ops, shape):
+    """W % 4 == 0 takes the register-marching kernels (risp_march.cuh): median 3x3 (replicate border) bit-exact, bilateral with
+    per-image window 3 / 1 (reflect-101, circular support), unsharp mask 5x5 -- strips with a partial last warp, one-lane
+    frames, chunk seams."""
+    N, H, W = shape
+    x = rand_img(N, H, W, 31, 0.0, 1.0)
+    x255 = x * 255
+    assert torch.equal(ops.median(dev(x255), 3).cpu(), O.denoise_median(x255, 3))
+    for k in (5, 7):
+        if H > k and W > k:
+            assert torch.equal(ops.median(dev(x255), k).cpu(), O.denoise_median(x255, k)), k
+    win = torch.tensor([3, 1, 3][:N], dtype=torch.int32)
+    sc, ss = torch.tensor([30., 12., 80.][:N]), torch.tensor([3., 50., 1.5][:N])
+    yb = ops.bilateral(dev(x255), dev(win), dev(sc), dev(ss), max_window=3)
+    assert maxabs(yb / 255, O.denoise_bilateral(x255, win, sc, ss) / 255) <= TOL
+    a = torch.tensor([[0.7], [1.5], [0.2]][:N])
+    if H > 2:
+        assert maxabs(ops.sharpen(dev(x), dev(a)), O.sharpen(x, a)) <= TOL
