@@ -67,7 +67,13 @@ def bind_to_gpu_numa_node(local_rank):
         import torch.cuda as tc
         prop = tc.get_device_properties(local_rank)
         bus = '%04x:%02x:%02x.0' % (getattr(prop, 'pci_domain_id', 0), prop.pci_bus_id, prop.pci_device_id)
-        node = int(open('/sys/bus/pci/devices/%s/numa_node' % bus).read().strip())
+        path = '/sys/bus/pci/devices/%s/numa_node' % bus
+        if not os.path.exists(path):
+            import subprocess
+            q = subprocess.run(['nvidia-smi', '-i', str(local_rank), '--query-gpu=pci.bus_id', '--format=csv,noheader'],
+                               capture_output=True, text=True, timeout=10).stdout.strip().lower()
+            path = '/sys/bus/pci/devices/%s/numa_node' % (q[4:] if len(q) > 12 else q)     # 00000000:1b:00.0 -> 0000:1b:00.0
+        node = int(open(path).read().strip())
         if node < 0:
             return None
         cpus = []
