@@ -121,6 +121,11 @@ int risp_bayer_blc_wb_bwd(const float* raw, const float* dout, float* draw, floa
  * sid_sony_ratio_rggb2bgr_dataset.py:133, gt/255. :134) but after the PCIe hop (5 instead of 16 B/px). */
 int risp_decode_codes(const void* src, float* dst, long long n, int bytes_per_code, float denom,
                       risp_stream_t stream);
+/* The loader's random crop fused with the decode (sid_sony_ratio_rggb2bgr_dataset.py:109-136: even-aligned crop of the
+ * full frame, then /16383): src (planes, H, W) codes on the device, dst (planes, h, w) fp32 = src[:, y0:y0+h, x0:x0+w]/denom.
+ * y0, x0 must be even for a Bayer plane (CFA phase); checked when require_even != 0. */
+int risp_crop_decode(const void* src, float* dst, int planes, int H, int W, int y0, int x0, int h, int w,
+                     int bytes_per_code, float denom, int require_even, risp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Fused fixed pipeline (isp_universal.py:210-232 / origin_universal.py:143-161 as ONE pass):
@@ -139,6 +144,14 @@ int risp_pipeline_mse_step(const float* raw, const float* gt, float* y_out, floa
                            const int* param_off, const int* iarg, int S, const float* params,
                            int param_stride, int P, void* workspace, size_t workspace_bytes,
                            risp_stream_t stream);
+
+/* Same single pass with nn.L1Loss (isp_model.py:44-49: pixel_criterion 'l1'): loss = mean |y - gt|.  Pre-instantiated chain
+ * signatures only (RISP_E_UNSUPPORTED otherwise: run demosaic + chain + risp_loss_* instead). */
+int risp_pipeline_l1_step(const float* raw, const float* gt, float* y_out, float* loss_out, float* dparams,
+                          int N, int H, int W, int dm_kind, float dm_clip_hi, const int* ops,
+                          const int* param_off, const int* iarg, int S, const float* params,
+                          int param_stride, int P, void* workspace, size_t workspace_bytes,
+                          risp_stream_t stream);
 
 /* Backward of risp_pipeline_fwd for an upstream gradient dy (N,3,H,W): recomputes the forward from
  * raw in registers (nothing was saved) and reduces d/dparams; 16 B/px.  No gradient w.r.t. raw: the
@@ -254,6 +267,13 @@ int risp_whole2patch(const float* frame, float* tiles, int C, int H, int W, int 
  * gather form (no atomics, deterministic).  clip01 != 0 also applies clip(.,0,1) (test_split.py:107) */
 int risp_patch2whole(const float* tiles, float* frame, int C, int H, int W, int h, int w, int sh, int sw,
                      const int* ys, int ny, const int* xs, int nx, int clip01, risp_stream_t stream);
+
+/* Same blend with the result also (or only: frame may be NULL) as 8-bit HWC -- `(np.clip(merged, 0, 1) * 255.).astype(np.uint8)`
+ * of test_split.py:107 fused into the blend, so the D2H copy of a 12 MP result is 36 MB instead of 144 MB. */
+int risp_patch2whole_u8(const float* tiles, float* frame, unsigned char* frame_u8, int C, int H, int W, int h, int w, int sh,
+                        int sw, const int* ys, int ny, const int* xs, int nx, risp_stream_t stream);
+/* tensor2bgr (utils/util.py:118-135) on the device: (C,H,W) fp32 -> (H,W,C) uint8 = trunc(clip(x*255, 0, 255)) */
+int risp_to_u8_hwc(const float* x, unsigned char* out, int C, int H, int W, risp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Dense convolution for the CNN candidates (srcnn_res_arch.py:15-24, srcnn_demosaic_arch.py:14-25,

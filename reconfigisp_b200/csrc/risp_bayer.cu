@@ -300,3 +300,36 @@ extern "C" int risp_decode_codes(const void* src, float* dst, long long n, int b
     decode_kernel<unsigned char><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const unsigned char*>(src), dst, n, denom);
   return check_launch("decode_kernel");
 }
+
+namespace risp {
+// crop + decode: dst[p][y][x] = src[p][y0+y][x0+x] / denom   (the loader's random crop after the PCIe hop)
+template <typename T>
+__global__ void __launch_bounds__(256)
+crop_decode_kernel(const T* __restrict__ src, float* __restrict__ dst, int H, int W, int y0, int x0, int h, int w, float denom) {
+  const long long plane_in = (long long)H * W, plane_out = (long long)h * w;
+  const T* s = src + (long long)blockIdx.y * plane_in;
+  float* d = dst + (long long)blockIdx.y * plane_out;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < plane_out; i += (long long)gridDim.x * 256) {
+    const int y = (int)(i / w), x = (int)(i - (long long)y * w);
+    d[i] = __fdiv_rn((float)s[(long long)(y0 + y) * W + x0 + x], denom);
+  }
+}
+}  // namespace risp
+
+extern "C" int risp_crop_decode(const void* src, float* dst, int planes, int H, int W, int y0, int x0, int h, int w,
+                                int bytes_per_code, float denom, int require_even, risp_stream_t stream) {
+  RISP_REQUIRE(src && dst && planes > 0 && planes <= 65535 && H > 0 && W > 0 && h > 0 && w > 0 && denom > 0.f, RISP_E_INVALID,
+               "risp_crop_decode: bad arguments");
+  RISP_REQUIRE(y0 >= 0 && x0 >= 0 && y0 + h <= H && x0 + w <= W, RISP_E_INVALID, "risp_crop_decode: crop %dx%d at (%d,%d) leaves the %dx%d frame",
+               h, w, y0, x0, H, W);
+  RISP_REQUIRE(bytes_per_code == 1 || bytes_per_code == 2, RISP_E_INVALID, "risp_crop_decode: 1 or 2 bytes per code");
+  RISP_REQUIRE(!require_even || ((y0 % 2 == 0) && (x0 % 2 == 0)), RISP_E_ALIGN,
+               "risp_crop_decode: a Bayer crop must start on an even row and column (CFA phase), got (%d,%d)", y0, x0);
+  long long g = cdiv((long long)h * w, 256), cap = (long long)sm_count() * 8;
+  dim3 grid((unsigned)(g > cap ? cap : g), (unsigned)planes);
+  if (bytes_per_code == 2)
+    crop_decode_kernel<unsigned short><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const unsigned short*>(src), dst, H, W, y0, x0, h, w, denom);
+  else
+    crop_decode_kernel<unsigned char><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const unsigned char*>(src), dst, H, W, y0, x0, h, w, denom);
+  return check_launch("crop_decode_kernel");
+}

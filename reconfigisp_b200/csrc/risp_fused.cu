@@ -22,7 +22,7 @@ namespace fused {
 
 __constant__ float g_cpar[kCSlots][kCRows][kCRowFloats];
 
-enum { MODE_FWD = 0, MODE_STEP = 1, MODE_BWD = 2 };
+enum { MODE_FWD = 0, MODE_STEP = 1, MODE_BWD = 2, MODE_STEP_L1 = 3 };   // STEP: MSE loss; STEP_L1: L1 loss (isp_model.py:44-49)
 constexpr int kWarps = 1;     // one warp per CTA: everything but the lane index is CTA-uniform (uniform datapath, no R2UR)
 constexpr int kStrip = 128;
 
@@ -240,6 +240,10 @@ struct Tail {
       // d loss / d y up to the constant 2/numel (applied by the finaliser).  lane_w = 1 for lanes inside the frame (1*x - t is
       // exactly x - t) and 0 for the lanes of the last strip that hang over the right edge (their t is 0): no divergent branch
       const float2 dd = __ffma2_rn(make_float2(lane_w, lane_w), x, make_float2(-tgt.x, -tgt.y));
+      if constexpr (MODE == MODE_STEP_L1) {      // nn.L1Loss: sum |y - t| ; gradient sign(y - t) (0 at equality), 1/numel later
+        loss = add2(loss, make_float2(fabsf(dd.x), fabsf(dd.y)));
+        return make_float2((dd.x > 0.f ? 1.f : 0.f) - (dd.x < 0.f ? 1.f : 0.f), (dd.y > 0.f ? 1.f : 0.f) - (dd.y < 0.f ? 1.f : 0.f));
+      }
       loss = fma2(dd, dd, loss);
       return dd;
     } else {
@@ -858,7 +862,7 @@ int fused_partial_rows_per_frame(int N, int H, int W) {
   return cpf * fused::kWarps;
 }
 
-// mode: 0 forward, 1 MSE step, 2 backward with upstream dy.  Returns RISP_OK, an error, or 1 when the chain is not handled.
+// mode: 0 forward, 1 MSE step, 2 backward with upstream dy, 3 L1 step.  Returns RISP_OK, an error, or 1 when the chain is not handled.
 // *rows_per_frame receives the number of partial rows per frame actually written (modes 1, 2).
 int fused_launch(int mode, const float* raw, const float* gt, float* y, float* partial, const float* params, int pstride,
                  int N, int H, int W, int dm_kind, float clip_hi, const ChainDesc& d, cudaStream_t st, int* rows_per_frame) {
@@ -876,10 +880,14 @@ int fused_launch(int mode, const float* raw, const float* gt, float* y, float* p
   const unsigned sig = chain_signature(d);
   Geometry g;
   if (mode == 0) return dispatch<MODE_FWD>(a, d, sig, N, dm_kind, st, nullptr);
-  rc = (mode == 1) ? dispatch<MODE_STEP>(a, d, sig, N, dm_kind, st, &g) : dispatch<MODE_BWD>(a, d, sig, N, dm_kind, st, &g);
+  auto go = [&](Geometry* gp) {
+    return (mode == 1) ? dispatch<MODE_STEP>(a, d, sig, N, dm_kind, st, gp)
+         : (mode == 3) ? dispatch<MODE_STEP_L1>(a, d, sig, N, dm_kind, st, gp) : dispatch<MODE_BWD>(a, d, sig, N, dm_kind, st, gp);
+  };
+  rc = go(&g);
   if (rc != RISP_OK) return rc;
   if (rows_per_frame) *rows_per_frame = g.cpf * kWarps;
-  return (mode == 1) ? dispatch<MODE_STEP>(a, d, sig, N, dm_kind, st, nullptr) : dispatch<MODE_BWD>(a, d, sig, N, dm_kind, st, nullptr);
+  return go(nullptr);
 }
 
 }  // namespace risp

@@ -37,8 +37,8 @@ __device__ __forceinline__ float ramp(int i, int n, int e) {
 }
 
 __global__ void __launch_bounds__(kT)
-patch2whole_kernel(const float* __restrict__ tiles, float* __restrict__ frame, int C, int H, int W, int h, int w,
-                   int eh, int ew, Origins o, int clip01) {
+patch2whole_kernel(const float* __restrict__ tiles, float* __restrict__ frame, unsigned char* __restrict__ frame_u8, int C, int H,
+                   int W, int h, int w, int eh, int ew, Origins o, int clip01) {
   const long long plane = (long long)H * W;
   for (long long p = (long long)blockIdx.x * kT + threadIdx.x; p < plane; p += (long long)gridDim.x * kT) {
     const int y = (int)(p / W), x = (int)(p % W);
@@ -64,7 +64,9 @@ patch2whole_kernel(const float* __restrict__ tiles, float* __restrict__ frame, i
       if (c < C) {
         float v = __fdiv_rn(acc[c], cnt);
         if (clip01) v = sat01(v);
-        frame[(long long)c * plane + p] = v;
+        if (frame) frame[(long long)c * plane + p] = v;
+        // (np.clip(x, 0, 1) * 255.).astype(np.uint8): truncation, HWC (test_split.py:107, utils/util.py:118-135)
+        if (frame_u8) frame_u8[p * C + c] = (unsigned char)(int)__fmul_rn(sat01(v), 255.f);
       }
     }
   }
@@ -115,7 +117,44 @@ extern "C" int risp_patch2whole(const float* tiles, float* frame, int C, int H, 
   long long plane = (long long)H * W;
   long long g = cdiv(plane, kT);
   long long cap = (long long)sm_count() * 16;
-  patch2whole_kernel<<<(int)(g > cap ? cap : g), kT, 0, as_stream(stream)>>>(tiles, frame, C, H, W, h, w, (h - sh) / 2,
+  patch2whole_kernel<<<(int)(g > cap ? cap : g), kT, 0, as_stream(stream)>>>(tiles, frame, nullptr, C, H, W, h, w, (h - sh) / 2,
                                                                            (w - sw) / 2, o, clip01);
   return check_launch("patch2whole_kernel");
+}
+
+extern "C" int risp_patch2whole_u8(const float* tiles, float* frame, unsigned char* frame_u8, int C, int H, int W, int h, int w,
+                                   int sh, int sw, const int* ys, int ny, const int* xs, int nx, risp_stream_t stream) {
+  RISP_REQUIRE(frame_u8 && tiles && C >= 1 && C <= 4 && h >= 1 && w >= 1 && h <= H && w <= W && sh >= 1 && sw >= 1 &&
+                   sh <= h && sw <= w,
+               RISP_E_INVALID, "risp_patch2whole_u8: bad arguments");
+  Origins o;
+  int rc = fill_origins(&o, "risp_patch2whole_u8", ys, ny, xs, nx, H, W, h, w);
+  if (rc != RISP_OK) return rc;
+  long long plane = (long long)H * W;
+  long long g = cdiv(plane, kT);
+  long long cap = (long long)sm_count() * 16;
+  patch2whole_kernel<<<(int)(g > cap ? cap : g), kT, 0, as_stream(stream)>>>(tiles, frame, frame_u8, C, H, W, h, w, (h - sh) / 2,
+                                                                           (w - sw) / 2, o, 1);
+  return check_launch("patch2whole_kernel");
+}
+
+namespace risp {
+// tensor2bgr on the device (utils/util.py:118-135): (C,H,W) float -> (H,W,C) uint8, clip(x*255, 0, 255) truncated
+__global__ void __launch_bounds__(kT)
+to_u8_hwc_kernel(const float* __restrict__ x, unsigned char* __restrict__ out, int C, long long HW) {
+  for (long long p = (long long)blockIdx.x * kT + threadIdx.x; p < HW; p += (long long)gridDim.x * kT) {
+    for (int c = 0; c < C; ++c) {
+      const float v = fminf(fmaxf(__fmul_rn(x[(long long)c * HW + p], 255.f), 0.f), 255.f);
+      out[p * C + c] = (unsigned char)(int)v;
+    }
+  }
+}
+}  // namespace risp
+
+extern "C" int risp_to_u8_hwc(const float* x, unsigned char* out, int C, int H, int W, risp_stream_t stream) {
+  RISP_REQUIRE(x && out && C >= 1 && C <= 4 && H > 0 && W > 0, RISP_E_INVALID, "risp_to_u8_hwc: bad arguments");
+  const long long HW = (long long)H * W;
+  long long g = cdiv(HW, kT), cap = (long long)sm_count() * 16;
+  to_u8_hwc_kernel<<<(int)(g > cap ? cap : g), kT, 0, as_stream(stream)>>>(x, out, C, HW);
+  return check_launch("to_u8_hwc_kernel");
 }

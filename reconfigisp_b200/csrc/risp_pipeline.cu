@@ -416,7 +416,7 @@ extern "C" size_t risp_pipeline_step_workspace(int N, int H, int W, int P) {
   return (size_t)N * rows * RISP_NSLOT * sizeof(float) + finalize_rows_workspace(N, RISP_NSLOT);
 }
 
-static int pipeline_step_impl(const char* who, bool gt_is_dy, const float* raw, const float* gt, float* y_out,
+static int pipeline_step_impl(const char* who, bool gt_is_dy, bool l1, const float* raw, const float* gt, float* y_out,
                               float* loss_out, float* dparams, int N, int H, int W, int dm_kind, float dm_clip_hi,
                               const int* ops, const int* param_off, const int* iarg, int S, const float* params,
                               int param_stride, int P, void* workspace, size_t workspace_bytes, risp_stream_t stream) {
@@ -443,7 +443,9 @@ static int pipeline_step_impl(const char* who, bool gt_is_dy, const float* raw, 
   float* partial = static_cast<float*>(workspace);
   void* fin_ws = reinterpret_cast<char*>(workspace) + (need - finalize_rows_workspace(N, RISP_NSLOT));
   int frows = 0;
-  rc = (P > 0 && use_fused()) ? fused_launch(gt_is_dy ? 2 : 1, raw, gt, y_out, partial, params, param_stride, N, H, W, dm_kind, dm_clip_hi, d, st, &frows) : 1;
+  RISP_REQUIRE(!l1 || (P > 0 && use_fused() && fused_handles(d, N, param_stride, H, W)), RISP_E_UNSUPPORTED,
+               "%s: the fused L1 step exists for the pre-instantiated chain signatures only (run the unfused path)", who);
+  rc = (P > 0 && use_fused()) ? fused_launch(gt_is_dy ? 2 : (l1 ? 3 : 1), raw, gt, y_out, partial, params, param_stride, N, H, W, dm_kind, dm_clip_hi, d, st, &frows) : 1;
   if (rc == 1) {
     PipeArgs a{raw, gt, y_out, partial, params, param_stride, H, W, 0, dm_clip_hi, gt_is_dy ? 1 : 0};
     rc = launch_pipeline<MODE_STEP>(a, d, N, dm_kind, big, st);
@@ -469,7 +471,7 @@ static int pipeline_step_impl(const char* who, bool gt_is_dy, const float* raw, 
     SlotList m;
     chain_slot_list(d, &m);
     return finalize_partials(partial, dparams, N, g.warps_per_image, RISP_NSLOT, P, m.dst, m.slot, m.n,
-                             gt_is_dy ? 1.f : (float)(2.0 / numel), shared_row, st);
+                             gt_is_dy ? 1.f : (float)((l1 ? 1.0 : 2.0) / numel), shared_row, st);
   }
   // loss and every parameter gradient in one launch (the loss rides along when all frames share one parameter row)
   const bool loss_inline = !gt_is_dy && shared_row;
@@ -482,7 +484,7 @@ static int pipeline_step_impl(const char* who, bool gt_is_dy, const float* raw, 
   SlotList m;
   chain_slot_list(d, &m);
   return finalize_rows(partial, fin_ws, dparams, loss_inline ? loss_out : nullptr, N, g.warps_per_image, RISP_NSLOT, P, m.dst,
-                       m.slot, m.n, gt_is_dy ? 1.f : (float)(2.0 / numel), (float)(1.0 / numel), RISP_SLOT_LOSS, shared_row, st);
+                       m.slot, m.n, gt_is_dy ? 1.f : (float)((l1 ? 1.0 : 2.0) / numel), (float)(1.0 / numel), RISP_SLOT_LOSS, shared_row, st);
 }
 
 extern "C" int risp_pipeline_mse_step(const float* raw, const float* gt, float* y_out, float* loss_out, float* dparams,
@@ -490,7 +492,7 @@ extern "C" int risp_pipeline_mse_step(const float* raw, const float* gt, float* 
                                       const int* param_off, const int* iarg, int S, const float* params,
                                       int param_stride, int P, void* workspace, size_t workspace_bytes,
                                       risp_stream_t stream) {
-  return pipeline_step_impl("risp_pipeline_mse_step", false, raw, gt, y_out, loss_out, dparams, N, H, W, dm_kind,
+  return pipeline_step_impl("risp_pipeline_mse_step", false, false, raw, gt, y_out, loss_out, dparams, N, H, W, dm_kind,
                             dm_clip_hi, ops, param_off, iarg, S, params, param_stride, P, workspace, workspace_bytes,
                             stream);
 }
@@ -499,6 +501,16 @@ extern "C" int risp_pipeline_bwd(const float* raw, const float* dy, float* dpara
                                  float dm_clip_hi, const int* ops, const int* param_off, const int* iarg, int S,
                                  const float* params, int param_stride, int P, void* workspace, size_t workspace_bytes,
                                  risp_stream_t stream) {
-  return pipeline_step_impl("risp_pipeline_bwd", true, raw, dy, nullptr, nullptr, dparams, N, H, W, dm_kind, dm_clip_hi,
+  return pipeline_step_impl("risp_pipeline_bwd", true, false, raw, dy, nullptr, nullptr, dparams, N, H, W, dm_kind, dm_clip_hi,
                             ops, param_off, iarg, S, params, param_stride, P, workspace, workspace_bytes, stream);
+}
+
+extern "C" int risp_pipeline_l1_step(const float* raw, const float* gt, float* y_out, float* loss_out, float* dparams,
+                                     int N, int H, int W, int dm_kind, float dm_clip_hi, const int* ops,
+                                     const int* param_off, const int* iarg, int S, const float* params,
+                                     int param_stride, int P, void* workspace, size_t workspace_bytes,
+                                     risp_stream_t stream) {
+  return pipeline_step_impl("risp_pipeline_l1_step", false, true, raw, gt, y_out, loss_out, dparams, N, H, W, dm_kind,
+                            dm_clip_hi, ops, param_off, iarg, S, params, param_stride, P, workspace, workspace_bytes,
+                            stream);
 }

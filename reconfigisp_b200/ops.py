@@ -60,6 +60,15 @@ class Chain:
         return self._ops, self._off, self._iarg, self.S
 
 
+_FUSED_SIGNATURES = (('gain', 'poly10', 'gamma', 'gtm'), ('gamma', 'poly10', 'gain'), ('gamma', 'poly10'), ('gamma', 'gtm'))
+
+
+def fused_chain_supported(chain):
+    """True when the packed single-pass kernels (csrc/risp_fused.cu) are instantiated for this chain: the sRGB tails of the
+    shipped pipelines (11_13_01_14, 01_13_11, 01_13, 01_14; 4-segment tone curve)."""
+    return tuple(chain.names) in _FUSED_SIGNATURES and all(i == 4 for n, i in zip(chain.names, chain.iargs) if n == 'gtm')
+
+
 def _param_table(params, N, P):
     """(N,P) or (1,P)/(P,) -> contiguous table and the ABI row stride (0 = shared row)."""
     if P == 0:
@@ -351,6 +360,30 @@ def decode_codes(codes, denom, out=None):
     return out
 
 
+def crop_decode(codes, y0, x0, h, w, denom, bayer=True):
+    """The loader's random crop + normalisation on the device (sid_sony_ratio_rggb2bgr_dataset.py:109-136): `codes`
+    (planes,H,W) or (N,C,H,W) uint8 / uint16 full frames already in HBM -> fp32 crop / denom.  A Bayer crop must start on an
+    even row and column (the reference aligns it the same way, s7isp_rggb2bgr_test_dataset.py:106-113)."""
+    if not codes.is_cuda:
+        raise RuntimeError('crop_decode runs on CUDA tensors only')
+    codes = codes.contiguous()
+    H, W = codes.shape[-2:]
+    planes = codes.numel() // (H * W)
+    out = torch.empty(tuple(codes.shape[:-2]) + (h, w), device=codes.device, dtype=torch.float32)
+    L.call('risp_crop_decode', L.ptr(codes), L.ptr(out), planes, H, W, int(y0), int(x0), int(h), int(w), codes.element_size(),
+           float(denom), int(bool(bayer)), L.stream())
+    return out
+
+
+def to_u8_hwc(x):
+    """`utils.util.tensor2bgr(tensor)` on the device: (C,H,W) or (1,C,H,W) fp32 -> (H,W,C) uint8 = trunc(clip(x*255, 0, 255))."""
+    x = (x[0] if x.dim() == 4 else x).detach().contiguous()
+    C, H, W = x.shape
+    out = torch.empty((H, W, C), device=x.device, dtype=torch.uint8)
+    L.call('risp_to_u8_hwc', L.ptr(x), L.ptr(out), C, H, W, L.stream())
+    return out
+
+
 # ---- stencils ---------------------------------------------------------------------------------------
 def bilateral(x, window, sigma_color, sigma_space, max_window=None):
     x = _img(x.detach(), 3)
@@ -553,8 +586,9 @@ def pipeline_fwd(raw, dm_kind, chain, params=None, clip_hi=1.0):
 class PipelineStep:
     """Pre-allocated state for repeated proxy-tuning steps on frames of one geometry."""
 
-    def __init__(self, N, H, W, dm_kind, chain, device, clip_hi=1.0, shared_row=True):
+    def __init__(self, N, H, W, dm_kind, chain, device, clip_hi=1.0, shared_row=True, l1=False):
         self.N, self.H, self.W, self.dm, self.chain, self.clip_hi = N, H, W, DM[dm_kind], chain, float(clip_hi)
+        self.entry = 'risp_pipeline_l1_step' if l1 else 'risp_pipeline_mse_step'    # nn.L1Loss / nn.MSELoss (isp_model.py:44-49)
         self.stride = 0 if shared_row else chain.P
         self.loss = torch.empty((1,), device=device, dtype=torch.float32)
         self.dparams = torch.empty((1 if shared_row else N, max(1, chain.P)), device=device, dtype=torch.float32)
@@ -562,7 +596,7 @@ class PipelineStep:
 
     def __call__(self, raw, gt, params, y_out=None):
         """-> (loss (1,), dparams).  raw (N,1,H,W), gt (N,3,H,W), params (1|N, P) kernel-level."""
-        L.call('risp_pipeline_mse_step', L.ptr(raw), L.ptr(gt), L.ptr(y_out), L.ptr(self.loss), L.ptr(self.dparams),
+        L.call(self.entry, L.ptr(raw), L.ptr(gt), L.ptr(y_out), L.ptr(self.loss), L.ptr(self.dparams),
                self.N, self.H, self.W, self.dm, self.clip_hi, *self.chain.desc(), L.ptr(params), self.stride,
                self.chain.P, L.ptr(self.ws), self.ws.numel() * 4, L.stream())
         return self.loss, self.dparams
@@ -572,11 +606,11 @@ class _PipelineMseFn(torch.autograd.Function):
     """loss = mse(pipeline(raw; params), gt) with d loss / d params from the same single pass."""
 
     @staticmethod
-    def forward(ctx, params, raw, gt, dm_kind, chain, clip_hi):
+    def forward(ctx, params, raw, gt, dm_kind, chain, clip_hi, l1=False):
         raw, gt = _img(raw, 1), _img(gt, 3)
         N, _, H, W = raw.shape
         tab, stride = _param_table(params, N, chain.P)
-        step = PipelineStep(N, H, W, dm_kind, chain, raw.device, clip_hi, shared_row=(stride == 0))
+        step = PipelineStep(N, H, W, dm_kind, chain, raw.device, clip_hi, shared_row=(stride == 0), l1=l1)
         loss, dpar = step(raw, gt, tab)
         ctx.pshape = params.shape
         ctx.save_for_backward(dpar)
@@ -585,11 +619,16 @@ class _PipelineMseFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         dpar, = ctx.saved_tensors
-        return (dpar * g).view(ctx.pshape), None, None, None, None, None
+        return (dpar * g).view(ctx.pshape), None, None, None, None, None, None
 
 
 def pipeline_mse(params, raw, gt, dm_kind, chain, clip_hi=1.0):
-    return _PipelineMseFn.apply(params, raw, gt, dm_kind, chain, clip_hi)
+    return _PipelineMseFn.apply(params, raw, gt, dm_kind, chain, clip_hi, False)
+
+
+def pipeline_l1(params, raw, gt, dm_kind, chain, clip_hi=1.0):
+    """mean |pipeline(raw; params) - gt| with d loss / d params from the same single pass (pre-instantiated chains)."""
+    return _PipelineMseFn.apply(params, raw, gt, dm_kind, chain, clip_hi, True)
 
 
 # ---- patches ----------------------------------------------------------------------------------------
@@ -610,6 +649,22 @@ def whole2patch(frame, size, stride):
     tiles = torch.empty((len(ys) * len(xs), C, h, w), device=f.device, dtype=torch.float32)
     L.call('risp_whole2patch', L.ptr(f), L.ptr(tiles), C, H, W, h, w, L.iarr(ys), len(ys), L.iarr(xs), len(xs), L.stream())
     return tiles, [(y, x) for y in ys for x in xs]
+
+
+def patch2whole_u8(tiles, frame_hw, stride, want_float=False):
+    """Blend + `(np.clip(merged, 0, 1) * 255.).astype(np.uint8)` (test_split.py:104-108) in one kernel -> (H,W,C) uint8
+    [, (C,H,W) fp32 clipped]."""
+    tiles = tiles.contiguous()
+    T, C, h, w = tiles.shape
+    H, W = frame_hw
+    sh, sw = stride
+    ys, xs = patch_origins(H, h, sh), patch_origins(W, w, sw)
+    assert T == len(ys) * len(xs)
+    out8 = torch.empty((H, W, C), device=tiles.device, dtype=torch.uint8)
+    outf = torch.empty((C, H, W), device=tiles.device, dtype=torch.float32) if want_float else None
+    L.call('risp_patch2whole_u8', L.ptr(tiles), L.ptr(outf), L.ptr(out8), C, H, W, h, w, sh, sw, L.iarr(ys), len(ys), L.iarr(xs),
+           len(xs), L.stream())
+    return (out8, outf) if want_float else out8
 
 
 def patch2whole(tiles, frame_hw, stride, clip01=False):

@@ -10,9 +10,10 @@ from . import dist as D
 from . import ops
 
 
-def split_inference(model_fn, frame, patch_size, patch_stride, chunk=None, clip01=True, out_channels=3):
+def split_inference(model_fn, frame, patch_size, patch_stride, chunk=None, clip01=True, out_channels=3, uint8=False):
     """frame: (1,C,H,W) or (C,H,W) CUDA tensor in [0,1]; model_fn: (T,C,h,w) -> (T,C',h,w).
-    Returns the blended (C',H,W) frame (clipped to [0,1] like test_split.py:107 when clip01)."""
+    Returns the blended (C',H,W) frame (clipped to [0,1] like test_split.py:107 when clip01), or with `uint8` the
+    (H,W,C') 8-bit image of test_split.py:107 packed by the blend kernel itself (4x less to copy back)."""
     f = frame[0] if frame.dim() == 4 else frame
     C, H, W = f.shape
     size, stride = (patch_size, patch_size), (patch_stride, patch_stride)
@@ -25,6 +26,8 @@ def split_inference(model_fn, frame, patch_size, patch_stride, chunk=None, clip0
             outs.append(model_fn(tiles[s:s + chunk]))
     out_tiles = torch.cat(outs) if len(outs) > 1 else outs[0]
     assert out_tiles.shape[1] == out_channels
+    if uint8:
+        return ops.patch2whole_u8(out_tiles.contiguous(), (H, W), stride)
     return ops.patch2whole(out_tiles.contiguous(), (H, W), stride, clip01=clip01)
 
 

@@ -131,12 +131,16 @@ class IspModel:
 
     # -- training step ---------------------------------------------------------------------------------------
     def _fused_loss(self):
-        plan = self.netG.fused_mse_step_plan() if (self.netG.fuse and self.loss_type == 'l2') else None
+        plan = self.netG.fused_mse_step_plan() if self.netG.fuse else None
         H, W = self.img.shape[2:]
         if plan is None or H % 2 or W % 4:
             return None
         dm_kind, chain, keep = plan
         table = self.netG._segment_table(keep, self.img.shape[0])
+        if self.loss_type == 'l1':
+            if not ops.fused_chain_supported(chain):
+                return None                                   # generic chains: unfused path with ops.l1_loss
+            return ops.pipeline_l1(table, self.img, self.gt, dm_kind, chain)
         return ops.pipeline_mse(table, self.img, self.gt, dm_kind, chain)
 
     def optimize_parameters(self):
@@ -169,7 +173,7 @@ class IspModel:
             seen.clear(); graphs.clear()
         # capture only once the same buffers / shapes / learning rates have been seen before (a loop that feeds fresh
         # device tensors every step would otherwise re-capture every step)
-        if seen.get(key, 0) < 2 or self._eager_steps < 2 or not (self.netG.fuse and self.loss_type == 'l2') or \
+        if seen.get(key, 0) < 2 or self._eager_steps < 2 or not self.netG.fuse or \
                 self.netG.fused_mse_step_plan() is None:
             return False
         try:

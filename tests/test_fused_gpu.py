@@ -184,3 +184,45 @@ def test_fused_saturated_pixels_clamp_masks(ops):
     lg = ops.pipeline_mse(pg, raw.cuda(), gt.cuda(), 'nearest', chain)
     dpg, = torch.autograd.grad(lg, pg)
     relclose(dpg, dpo)
+
+
+@pytest.mark.parametrize('sig', sorted(SIGS))
+def test_fused_l1_step(ops, sig):
+    """pixel_criterion 'l1' (isp_model.py:44-49) through the same single pass: loss and gradients vs the fp64 oracle."""
+    N, H, W = 2, 24, 264
+    g = torch.Generator().manual_seed(77)
+    raw, gt = torch.rand(N, 1, H, W, generator=g), torch.rand(N, 3, H, W, generator=g)
+    st = SIGS[sig]
+    chain = ops.Chain(st)
+    assert ops.fused_chain_supported(chain)
+    params = stage_params(st, g)
+    po = params.double().requires_grad_()
+    lo = (oracle_chain(O.demosaic_bilinear(raw.double()), st, po.expand(N, -1)) - gt.double()).abs().mean()
+    dpo, = torch.autograd.grad(lo, po)
+    pg = params.cuda().requires_grad_()
+    lg = ops.pipeline_l1(pg, raw.cuda(), gt.cuda(), 'bilinear', chain)
+    dpg, = torch.autograd.grad(lg, pg)
+    assert abs(float(lg.detach()) - float(lo.detach())) <= 1e-5
+    relclose(dpg, dpo)
+
+
+def test_uint8_pack_and_crop_decode(ops):
+    """tensor2bgr on the device (utils/util.py:118-135: clip(x*255, 0, 255) truncated, HWC), the u8 output of the blend
+    (test_split.py:107) and the loader's even-aligned crop + /16383 (sid_sony_ratio_rggb2bgr_dataset.py:109-136): bit-exact."""
+    import numpy as np
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(3, 37, 52, generator=g) * 1.2 - 0.1
+    ref = np.clip(np.transpose(x.numpy(), [1, 2, 0]) * 255, 0, 255).astype(np.uint8)
+    assert np.array_equal(ops.to_u8_hwc(x.cuda()).cpu().numpy(), ref)
+    H, W, ps, st = 120, 136, 48, 40
+    frame = torch.rand(3, H, W, generator=g) * 1.1 - 0.05
+    tiles, _ = ops.whole2patch(frame.cuda(), (ps, ps), (st, st))
+    merged = ops.patch2whole(tiles, (H, W), (st, st), clip01=True).cpu()
+    u8, f = ops.patch2whole_u8(tiles, (H, W), (st, st), want_float=True)
+    assert torch.equal(f.cpu(), merged)
+    assert np.array_equal(u8.cpu().numpy(), (np.clip(np.transpose(merged.numpy(), [1, 2, 0]), 0, 1) * 255.).astype(np.uint8))
+    codes = torch.randint(0, 16384, (2, 1, 60, 80), generator=g, dtype=torch.int32).to(torch.int16)
+    crop = ops.crop_decode(codes.cuda(), 12, 34, 32, 40, 16383.)
+    assert torch.equal(crop.cpu(), codes[:, :, 12:44, 34:74].float() / 16383.)
+    with pytest.raises(ValueError):
+        ops.crop_decode(codes.cuda(), 13, 34, 32, 40, 16383.)        # odd origin breaks the CFA phase
