@@ -79,6 +79,12 @@ int risp_chain_fwd(const float* x, float* y, int N, long long HW, const int* ops
                    const int* iarg, int S, const float* params, int param_stride, float in_scale,
                    float out_scale, risp_stream_t stream);
 
+/* Kernel-level parameter row of a fixed pipeline from its trainable logits, table[i] = a[i]*sigmoid(logits[i]) + b[i] (the
+ * wrappers' range mappings: gain = p*5 tools_origin.py:214, P = p*10-5 :326, gamma / knots = p), and the way back,
+ * dlogits[i] = dtable[i]*a[i]*s*(1-s).  All DEVICE arrays of length P. */
+int risp_param_table_fwd(const float* logits, const float* a, const float* b, float* table, int P, risp_stream_t stream);
+int risp_param_table_bwd(const float* logits, const float* a, const float* dtable, float* dlogits, int P, risp_stream_t stream);
+
 /* Backward of the chain: dx (nullable) and dparams.  dparams is (N,P) when param_stride==P and
  * (1,P) when param_stride==0; it is fully overwritten.  Deterministic (no float atomics).
  * Returns RISP_E_UNSUPPORTED if the chain holds a forward-only op. */

@@ -293,3 +293,37 @@ extern "C" int risp_chain_bwd(const float* x, const float* dy, float* dx, float*
   }
   return rc;
 }
+
+// ---- parameter table of a fixed pipeline: kernel-level values from the trainable logits, and back -----------------------
+// The wrappers map sigmoid(logit) affinely into each stage's range (gain = p*5 tools_origin.py:214, P = p*10-5 :326, gamma
+// and tone-curve knots = p).  One launch builds the whole (1,P) table, one launch turns d loss / d table into d loss / d logits:
+// the proxy-tuning step then needs no autograd graph at all (isp_model.py:128-142 as 7 launches instead of ~25).
+namespace risp {
+__global__ void param_table_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ a, const float* __restrict__ b,
+                                       float* __restrict__ table, int P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P) table[i] = fmaf(a[i], 1.f / (1.f + expf(-logits[i])), b[i]);
+}
+__global__ void param_table_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ a,
+                                       const float* __restrict__ dtable, float* __restrict__ dlogits, int P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P) {
+    const float s = 1.f / (1.f + expf(-logits[i]));
+    dlogits[i] = dtable[i] * a[i] * s * (1.f - s);
+  }
+}
+}  // namespace risp
+
+extern "C" int risp_param_table_fwd(const float* logits, const float* a, const float* b, float* table, int P,
+                                    risp_stream_t stream) {
+  RISP_REQUIRE(logits && a && b && table && P > 0, RISP_E_INVALID, "risp_param_table_fwd: bad arguments");
+  param_table_fwd_kernel<<<(int)cdiv(P, 128), 128, 0, as_stream(stream)>>>(logits, a, b, table, P);
+  return check_launch("param_table_fwd_kernel");
+}
+
+extern "C" int risp_param_table_bwd(const float* logits, const float* a, const float* dtable, float* dlogits, int P,
+                                    risp_stream_t stream) {
+  RISP_REQUIRE(logits && a && dtable && dlogits && P > 0, RISP_E_INVALID, "risp_param_table_bwd: bad arguments");
+  param_table_bwd_kernel<<<(int)cdiv(P, 128), 128, 0, as_stream(stream)>>>(logits, a, dtable, dlogits, P);
+  return check_launch("param_table_bwd_kernel");
+}

@@ -130,6 +130,69 @@ class IspModel:
         return ops.decode_codes(codes, denom, out=dst)
 
     # -- training step ---------------------------------------------------------------------------------------
+    def _fast_plan(self):
+        """The whole step without an autograd graph: [logits -> table] -> single-pass fused step -> [d table -> d logits]
+        written straight into the flat gradient buffer.  Possible when the pipeline fuses into one head (classical demosaic
+        + per-pixel stages the packed kernels are instantiated for) and every stage maps sigmoid(logit) affinely into its
+        range.  Built once; returns None when the pipeline does not qualify."""
+        if hasattr(self, '_fast'):
+            return self._fast
+        self._fast = None
+        plan = self.netG.fused_mse_step_plan() if self.netG.fuse else None
+        if plan is None or not ops.fused_chain_supported(plan[1]):
+            return None
+        dm_kind, chain, keep = plan
+        a, b, params = [], [], []
+        for k in keep:
+            p, mod = self.netG.all_params[k], self.netG.all_modules[k]
+            n = p.numel()
+            if n == 0:
+                continue
+            with torch.no_grad():
+                k0 = mod.kernel_params(torch.zeros(1, n, device=self.device))
+                k1 = mod.kernel_params(torch.ones(1, n, device=self.device))
+                kh = mod.kernel_params(torch.full((1, n), 0.5, device=self.device))
+            if k0 is None or k0.numel() != n or not torch.allclose(kh, 0.5 * (k0 + k1), atol=1e-6):
+                return None                                   # not an element-wise affine mapping
+            a.append((k1 - k0).reshape(-1)); b.append(k0.reshape(-1)); params.append(p)
+        covered = {id(p) for p in params}
+        if any(p.numel() > 0 and id(p) not in covered for p in self.netG.trainable_parameters) or not params:
+            return None
+        # the covered logits become views of ONE flat buffer, in table order (state-dict keys and Parameter objects unchanged)
+        flat = torch.cat([p.detach().reshape(-1) for p in params]).contiguous()
+        grad = torch.zeros_like(flat)
+        o = 0
+        for p in params:
+            n = p.numel()
+            p.data = flat[o:o + n].view_as(p)
+            p.grad = grad[o:o + n].view_as(p)
+            o += n
+        self._flat_grad = grad
+        P = flat.numel()
+        assert P == chain.P
+        self._fast = dict(dm=dm_kind, chain=chain, logits=flat, grad=grad, a=torch.cat(a).contiguous(), b=torch.cat(b).contiguous(),
+                          table=torch.empty((1, P), device=self.device), steps={})
+        return self._fast
+
+    def _fast_loss_and_grads(self):
+        f = self._fast_plan()
+        H, W = self.img.shape[2:]
+        if f is None or H % 2 or W % 4 or self.loss_type not in ('l1', 'l2'):
+            return False
+        from . import _lib as L
+        N = self.img.shape[0]
+        key = (N, H, W)
+        step = f['steps'].get(key)
+        if step is None:
+            step = f['steps'][key] = ops.PipelineStep(N, H, W, f['dm'], f['chain'], self.device, l1=(self.loss_type == 'l1'))
+        P = f['logits'].numel()
+        L.call('risp_param_table_fwd', L.ptr(f['logits']), L.ptr(f['a']), L.ptr(f['b']), L.ptr(f['table']), P, L.stream())
+        loss, dtable = step(self.img, self.gt, f['table'])
+        L.call('risp_param_table_bwd', L.ptr(f['logits']), L.ptr(f['a']), L.ptr(dtable), L.ptr(f['grad']), P, L.stream())
+        self.l_pix = loss.view(())
+        self.log_dict['loss'] = self.l_pix             # device scalar; `.item()` it when logging
+        return True
+
     def _fused_loss(self):
         plan = self.netG.fused_mse_step_plan() if self.netG.fuse else None
         H, W = self.img.shape[2:]
@@ -203,6 +266,8 @@ class IspModel:
             return False
 
     def _loss_and_grads(self):
+        if self.opt.get('fast_step', True) and self._fast_loss_and_grads():
+            return
         l_pix = self._fused_loss()
         if l_pix is None:
             self._output = self.netG(self.img)

@@ -273,3 +273,41 @@ def test_relu_gradient_outliers_are_mask_flips(golden):
     assert not bool((outlier & ~allowed).any()), 'gradient outliers away from any near-zero pre-activation'
     assert float(err[~allowed].max() if bool((~allowed).any()) else 0.0) <= 2e-4 * scale
     assert float(err.max()) <= 2e-2 * scale
+
+
+@pytest.mark.parametrize('crit', ['l2', 'l1'])
+def test_tuning_fast_step_matches_autograd_step(crit):
+    """The graph-free tuning step ([logits -> table] kernel, single-pass fused step, [d table -> d logits] kernel, flat
+    gradient buffer) against the autograd formulation of the same step (`fast_step: False`): losses and parameters after
+    several Adam updates, MSE and L1 (isp_model.py:44-49, :128-142)."""
+    from reconfigisp_b200.tuning import IspModel
+    from reconfigisp_b200.synthetic import synthetic_frames
+
+    def opt(fast):
+        return {'model': 'isp', 'is_train': True, 'cuda_graph': False, 'fast_step': fast,
+                'network_G': {'which_model_G': 'OriginUniversal', 'architecture': 'Bayer_02_Demosaic_02_sRGB_11_13_01_14', 'weight_seed': 10},
+                'train': {'lr_G': 1e-2, 'beta1': 0.9, 'beta2': 0.99, 'pixel_criterion': crit, 'lr_scheme': 'MultiStepLR',
+                          'lr_steps': [1000], 'lr_gamma': 0.5}, 'path': {'pretrain_model_G': None}}
+    raw, gt = synthetic_frames(2, 64, 96, seed=5)
+    models = [IspModel(opt(True)), IspModel(opt(False))]
+    losses, grads0 = [[], []], [None, None]
+    for k, m in enumerate(models):
+        m.feed_data((raw.cuda(), gt.cuda()))
+        for step in range(5):
+            m.optimize_parameters()
+            losses[k].append(float(m.log_dict['loss'].detach()))
+            if step == 0:
+                grads0[k] = [p.grad.detach().clone() for p in m.netG.trainable_parameters if p.numel()]
+    assert models[0]._fast is not None and getattr(models[1], '_fast', None) is None
+    # the first step is the same function evaluated two ways: loss identical, gradients to rounding
+    assert abs(losses[0][0] - losses[1][0]) <= 1e-7
+    for ga, gb in zip(*grads0):
+        relclose(ga, gb, rtol=2e-5, atol=1e-9)
+    # afterwards Adam (lr 1e-2, update ~ lr * g / |g| in the first steps) amplifies those roundings: trajectories stay close
+    assert max(abs(a - b) for a, b in zip(*losses)) <= 2e-3 * max(losses[1]), losses
+    for pa, pb in zip(models[0].netG.trainable_parameters, models[1].netG.trainable_parameters):
+        if pa.numel():
+            assert maxabs(pa.detach(), pb.detach()) <= 2e-3
+    # state-dict keys and shapes are untouched by the flat re-layout
+    sa, sb = models[0].netG.state_dict(), models[1].netG.state_dict()
+    assert list(sa.keys()) == list(sb.keys()) and all(sa[k].shape == sb[k].shape for k in sa)
