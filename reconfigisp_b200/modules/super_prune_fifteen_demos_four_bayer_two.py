@@ -14,6 +14,8 @@ Mixed-op evaluation (reference :175-214) re-designed for the device:
   * quirks kept: mask from detached probs and detached normaliser (:188-192), zero (not None) gradients for
     the parameters of pruned candidates (:199-201), Skip aliasing, GtmManual using batch row 0.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -103,6 +105,8 @@ class SuperPruneFifteenDemosFourBayerTwo(nn.Module):
         # like the reference, the per-step containers are plain Python lists: candidate-net weights stay out
         # of named_parameters()/state_dict()/DDP
         self._chain = ops.Chain([op for _, op in SRGB_CLASSICAL])
+        self.n_streams = int(os.environ.get('RISP_SEARCH_STREAMS', '4'))
+        self._streams = []
 
     def _apply(self, fn, *a, **k):
         super()._apply(fn, *a, **k)
@@ -133,9 +137,36 @@ class SuperPruneFifteenDemosFourBayerTwo(nn.Module):
                 z = t if z is None else z + t
         return z
 
+    # ------------------------------------------------------------------------------------------------------
+    def _fan_out(self, jobs):
+        """Run the materialised (CNN) candidates of one step: jobs = [callable -> tensor].  With `self.n_streams` > 1 they are
+        spread over side streams -- the candidates of a step are independent (reference :195-210 evaluates them one after the
+        other), and at the reference's 4 x 256^2 batch a single candidate's grid leaves a partial last wave on 148 SMs, which
+        the other candidates' CTAs fill.  Autograd replays each candidate's backward on the stream its forward ran on."""
+        n = min(self.n_streams, len(jobs)) if self._small_batch else 1      # big batches fill the SMs on their own (and
+        if n <= 1 or not torch.cuda.is_available():                          # per-stream allocator pools would cost HBM)
+            return [j() for j in jobs]
+        main = torch.cuda.current_stream()
+        if len(self._streams) < n:
+            self._streams += [torch.cuda.Stream() for _ in range(n - len(self._streams))]
+        fork = torch.cuda.Event()
+        fork.record(main)
+        outs = []
+        for k, job in enumerate(jobs):
+            s = self._streams[k % n]
+            s.wait_event(fork)
+            with torch.cuda.stream(s):
+                outs.append(job())
+        for s in self._streams[:n]:
+            main.wait_stream(s)
+        for o in outs:
+            o.record_stream(main)
+        return outs
+
     def forward(self, x):
         """x: (N,1,H,W) RGGB -> (N,3,H,W) BGR."""
         N = x.size(0)
+        self._small_batch = x.numel() <= (1 << 20)
         self.middle_results = []
         posts = self._post_probs()
 
@@ -155,12 +186,13 @@ class SuperPruneFifteenDemosFourBayerTwo(nn.Module):
         # ---- demosaic step: every candidate maps 1 -> 3 planes, all are materialised ---------------------------
         post, host = posts[1]
         mods = self.all_modules[1]
-        ext, widx = [], []
+        jobs, widx = [], []
         for k in range(4):
             if host[k] < 1e-9:
                 continue
-            ext.append(mods[k](x, None))
+            jobs.append(lambda k=k, x=x: mods[k](x, None))
             widx.append(k)
+        ext = self._fan_out(jobs)
         y = ops.mixed_op(ext[0].detach(), ops.Chain([]), None, post[widx], ext)
         self.middle_results.append(y)
         x = y
@@ -175,15 +207,16 @@ class SuperPruneFifteenDemosFourBayerTwo(nn.Module):
             gw = grayworld_gains(x) if not host[4] < 1e-9 else torch.ones((N, 3), device=x.device)
             table = torch.cat([sig(0).expand(N, 1), gw, (sig(10) * 5).expand(N, 3), (sig(12) * 10 - 5).expand(N, 30),
                                sig(13).expand(N, 3)], dim=1)
-            ext, widx = [], list(cls_idx)
+            jobs, widx = [], list(cls_idx)
             pruned = [i for i in range(15) if host[i] < 1e-9]
             for i in range(15):
                 if i in cls_idx or host[i] < 1e-9:
                     continue
                 par = pars[i]
                 par_tensor = None if par.nelement() == 0 else torch.sigmoid(par).repeat(N, 1)
-                ext.append(mods[i](x, par_tensor))
+                jobs.append(lambda i=i, x=x, p=par_tensor: mods[i](x, p))
                 widx.append(i)
+            ext = self._fan_out(jobs)
             w = post[widx]
             dummy = self._dummy(pars, pruned)
             if dummy is not None:
