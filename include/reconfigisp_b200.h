@@ -175,6 +175,11 @@ size_t risp_plane_stats_workspace(int planes, long long HW);
 /* out: (planes, 3) = min, mean, max of every plane */
 int risp_plane_stats(const float* x, float* out, int planes, long long HW, void* workspace,
                      size_t workspace_bytes, risp_stream_t stream);
+/* idx: (planes, 2) int32 = row-major position of the FIRST minimum / maximum of every plane -- the pixel that
+ * torch.min(x, dim=3) -> torch.min(.., dim=2) (srcnn_res_arch.py:36-40) routes its gradient to; stats from risp_plane_stats */
+int risp_plane_argfirst(const float* x, const float* stats, int* idx, int planes, long long HW, risp_stream_t stream);
+/* dx (planes, HW) = backward of [min, mean, max]: g (planes, 3) upstream gradients, idx from risp_plane_argfirst */
+int risp_plane_stats_bwd(const float* g, const int* idx, float* dx, int planes, long long HW, risp_stream_t stream);
 /* out: (N,) mean over pixels of log(1e-6 + lum(scale*x)) for BGR images (reinhard) */
 int risp_loglum_mean(const float* x, float* out, int N, long long HW, float scale, void* workspace,
                      size_t workspace_bytes, risp_stream_t stream);
@@ -309,7 +314,7 @@ int risp_conv2d_bwd_weight(const float* x, const float* dy, const float* mask_dy
 
 /* Tensor-core path of the same convolution: implicit GEMM on tcgen05 (kind::tf32, TMEM accumulators) with a
  * 3-term hi/lo split so the result stays fp32-accurate (<= ~1e-6 relative), on CHANNEL-BLOCKED activations
- * (N, H, C16/4, W, 4) where C16 = channels padded to a multiple of 16 (risp_conv_tc_padded_channels).
+ * (N, H, C4/4, W, 4) where C4 = channels padded to a multiple of 4 (risp_conv_tc_padded_channels).
  * risp_to_blocked / risp_from_blocked convert from / to planar NCHW.  Same flags and mask semantics as
  * risp_conv2d_fwd; the output goes to the blocked tensor and/or a planar NCHW tensor (either may be NULL). */
 int risp_conv_tc_supported(int Cin, int Cout, int K);
@@ -322,6 +327,18 @@ int risp_from_blocked(const float* blocked, float* planar, int N, int C, int CG,
 int risp_conv_tc_fwd(const float* x_blk, const float* mask_in_blk, const float* wprep, const float* bias,
                      const float* res_blk, const float* mask_out_blk, float* y_blk, float* y_planar, int N, int Cin,
                      int Cout, int H, int W, int K, int flags, risp_stream_t stream);
+/* The same with a position-dependent bias: bias_tab (N, K*K, pad16(Cout)) is indexed by the border class of the output
+ * pixel (class = min(y, PAD) from the top, K-1 - min(H-1-y, PAD) from the bottom, likewise in x; needs H, W >= K-1).
+ * This is how SRCNNRes' spatially constant input channels (per-image min/mean/max and parameters broadcast over the
+ * frame, srcnn_res_arch.py:36-48) are folded out of its first convolution: their contribution is a per-image bias that
+ * only differs where the zero padding cuts taps off.  risp_blocked_class_sums is the backward of that table: the sums
+ * of a blocked gradient (masked by [mask > 0] if given) over the pixels of every class, out (N, K, K, CP). */
+int risp_conv_tc_fwd_tab(const float* x_blk, const float* mask_in_blk, const float* wprep, const float* bias,
+                         const float* bias_tab, const float* res_blk, const float* mask_out_blk, float* y_blk,
+                         float* y_planar, int N, int Cin, int Cout, int H, int W, int K, int flags, risp_stream_t stream);
+size_t risp_blocked_class_sums_workspace(int N, int C, int H, int K);
+int risp_blocked_class_sums(const float* g_blk, const float* mask_blk, float* out, int N, int C, int CP, int H, int W, int K,
+                            void* workspace, size_t workspace_bytes, risp_stream_t stream);
 
 /* Diagnostic: cycles to issue / complete `iters` tcgen05 tf32 MMAs (M=128, N=NP, K=8) from one thread with the
  * operand layout of risp_conv_tc_fwd.  out: DEVICE long long[2] = {issue cycles, total cycles}. */

@@ -26,12 +26,15 @@ struct ConvTcArgs {
   const float* x;        // blocked (N, H, CinG, W, 4)
   const float* wprep;    // [chunk][dy][dx][kg][CoutPad][4] hi, then the same again for lo
   const float* bias;     // nullable (Cout)
+  const float* bias_tab; // nullable (N, K*K, CoutPad): bias by border class of the output pixel (SRCNNRes' folded constant channels)
   const float* res;      // nullable, blocked (N, H, CoutG, W, 4)
   const float* mask_in;  // nullable, blocked like x: x is multiplied by [mask_in > 0] while staging (backward of an output ReLU)
   const float* mask_out; // nullable, blocked like y: the result is multiplied by [mask_out > 0] (backward of an input ReLU)
   float* y_blk;          // nullable, blocked (N, H, CoutG, W, 4)
   float* y_pln;          // nullable, planar (N, Cout, H, W)
   int CinG, Cout, CoutPad, H, W, flags;
+  int Cin;               // real input channels: only ceil(Cin/8) chunks are multiplied (the rest of the layout is zero padding)
+  int w_chunks;          // chunks the weights were prepared with (the lo block follows the hi block of ALL chunks)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------
@@ -209,12 +212,12 @@ conv_tc_kernel(ConvTcArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int n_chunks = (a.CinG * 4 + CI_C - 1) / CI_C;
+  const int n_chunks = (a.Cin + CI_C - 1) / CI_C;
   const int n_stages = n_chunks * C::NST;
   const long long row_stride = (long long)a.CinG * a.W * 4;              // floats per image row (blocked layout)
   const float* xin = a.x + (long long)n * a.H * row_stride;
   const float* min_ = a.mask_in ? a.mask_in + (long long)n * a.H * row_stride : nullptr;
-  const long long lo_off = (long long)n_chunks * C::B_CHUNK_FLOATS;
+  const long long lo_off = (long long)a.w_chunks * C::B_CHUNK_FLOATS;
   constexpr uint32_t kStageBytes = C::B_STAGE_FLOATS * 4;
 
   // weight stage s -> buffer s % NBUF (hi block then lo block); issued by the MMA lane only
@@ -421,8 +424,11 @@ conv_tc_kernel(ConvTcArgs a) {
              res_relu = (a.flags & RISP_CONV_RES_RELU) != 0;
   const int lq = warp & 3, half = warp >> 2;
   const int gx = x0 + lq * 32 + lane;
-  const int CoutG = a.CoutPad / 4;
+  const int CoutG = (a.Cout + 3) / 4;                   // groups of the blocked output / residual / mask (layout: ceil(C/4))
   const long long orow = (long long)CoutG * a.W * 4;
+  // border class of the output pixel (bias table): taps that fall outside the frame see zero padding, so the folded
+  // contribution of a spatially constant channel depends on which of the K x K border classes the pixel is in
+  const int xcls = gx < C::PAD ? gx : (gx >= a.W - C::PAD ? K - (a.W - gx) : C::PAD);
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int gy = y0 + r;                              // warp-uniform
@@ -437,12 +443,15 @@ conv_tc_kernel(ConvTcArgs a) {
 #pragma unroll
       for (int q = 0; q < 16; ++q) v[q] += vc[q];
       if (gy < a.H && gx < a.W) {
+        const int ycls = gy < C::PAD ? gy : (gy >= a.H - C::PAD ? K - (a.H - gy) : C::PAD);
+        const float* btab = a.bias_tab ? a.bias_tab + ((long long)n * K * K + ycls * K + xcls) * a.CoutPad : nullptr;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int co = cb * 16 + q * 4;
+          if (co >= CoutG * 4) continue;                 // padding groups are not part of the layout
           float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
           {
-            const float4 bb = *reinterpret_cast<const float4*>(s_bias + co);
+            const float4 bb = btab ? __ldg(reinterpret_cast<const float4*>(btab + co)) : *reinterpret_cast<const float4*>(s_bias + co);
             o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
           }
           if (relu_out) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
@@ -537,6 +546,58 @@ __global__ void from_blocked_kernel(const float* __restrict__ src, float* __rest
   }
 }
 
+// ---- gradient of the bias table: sums of a blocked gradient over the K x K border classes of its pixels -----------------
+// Pass 1: one CTA per (row, image): for every channel group the interior columns are summed by a warp, the 2*PAD border
+// columns are copied -> partial (N, H, K, CG*4).  Pass 2: rows folded into their K classes -> out (N, K, K, CP) with
+// CP >= CG*4 (padding channels zero).  Fixed summation order (bit-reproducible).
+__global__ void __launch_bounds__(256)
+class_sums_rows_kernel(const float* __restrict__ g, const float* __restrict__ mask, float* __restrict__ partial, int CG, int H, int W,
+                       int K) {
+  const int y = blockIdx.x, n = blockIdx.y, PAD = K / 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = ((long long)n * H + y) * CG * W;                // float4 elements
+  const float4* gr = reinterpret_cast<const float4*>(g) + row;
+  const float4* mr = mask ? reinterpret_cast<const float4*>(mask) + row : nullptr;
+  float4* out = reinterpret_cast<float4*>(partial) + ((long long)n * H + y) * K * CG;
+  auto load = [&](int cg, int x) {
+    float4 v = __ldg(gr + (long long)cg * W + x);
+    if (mr) {
+      const float4 m = __ldg(mr + (long long)cg * W + x);
+      v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f; v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+    }
+    return v;
+  };
+  for (int cg = warp; cg < CG; cg += 8) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int x = PAD + lane; x < W - PAD; x += 32) {
+      const float4 v = load(cg, x);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
+    if (lane == 0) out[PAD * CG + cg] = acc;
+    if (lane < 2 * PAD) {
+      const int x = lane < PAD ? lane : W - 2 * PAD + lane;               // classes 0..PAD-1 and PAD+1..K-1
+      const int cls = lane < PAD ? lane : lane + 1;
+      out[cls * CG + cg] = load(cg, x);
+    }
+  }
+}
+
+__global__ void class_sums_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int CG, int H, int K, int CP) {
+  // grid (K y-classes, N); threads over (x-class, channel)
+  const int ycls = blockIdx.x, n = blockIdx.y, PAD = K / 2, C4 = CG * 4;
+  for (int i = threadIdx.x; i < K * CP; i += blockDim.x) {
+    const int xcls = i / CP, c = i % CP;
+    float acc = 0.f;
+    if (c < C4) {
+      const int y0 = ycls < PAD ? ycls : (ycls == PAD ? PAD : H - K + ycls);
+      const int y1 = ycls == PAD ? H - PAD : y0 + 1;
+      for (int y = y0; y < y1; ++y) acc += partial[(((long long)n * H + y) * K + xcls) * C4 + c];
+    }
+    out[(((long long)n * K + ycls) * K + xcls) * CP + c] = acc;
+  }
+}
+
 template <int K, int CI_C, int R, int NP, int NBUF, int MINB, int ABUF, int PF, int DXS>
 static int launch_tc(const ConvTcArgs& a, int N, cudaStream_t st) {
   using C = TcCfg<K, CI_C, R, NP, NBUF, MINB, ABUF, PF, DXS>;
@@ -564,7 +625,7 @@ extern "C" int risp_conv_tc_supported(int Cin, int Cout, int K) {
   return (K == 1 || K == 3 || K == 5 || K == 9) && Cout <= 64 && Cin >= 1;
 }
 
-extern "C" int risp_conv_tc_padded_channels(int C) { return (C + 15) / 16 * 16; }
+extern "C" int risp_conv_tc_padded_channels(int C) { return (C + 3) / 4 * 4; }
 
 extern "C" size_t risp_conv_tc_weight_floats(int Cin, int Cout, int K, int transpose_flip) {
   const int rows = transpose_flip ? Cout : Cin, cols = transpose_flip ? Cin : Cout;
@@ -598,16 +659,44 @@ extern "C" int risp_from_blocked(const float* blocked, float* planar, int N, int
   return check_launch("from_blocked_kernel");
 }
 
+extern "C" size_t risp_blocked_class_sums_workspace(int N, int C, int H, int K) {
+  return (N > 0 && C > 0 && H > 0 && K > 0) ? sizeof(float) * (size_t)N * H * K * ((C + 3) / 4 * 4) : 0;
+}
+
+// out (N, K, K, CP): sums of g (blocked, ceil(C/4) groups; optionally masked by [mask > 0]) over the pixels of every border class
+extern "C" int risp_blocked_class_sums(const float* g_blk, const float* mask_blk, float* out, int N, int C, int CP, int H, int W, int K,
+                                       void* workspace, size_t workspace_bytes, risp_stream_t stream) {
+  RISP_REQUIRE(g_blk && out && N > 0 && N <= 65535 && C > 0 && CP >= (C + 3) / 4 * 4 && (K & 1) && K >= 1 && K <= 15 && H >= K - 1 &&
+                   W >= K - 1 && H <= 65535, RISP_E_INVALID, "risp_blocked_class_sums: bad arguments");
+  RISP_REQUIRE(workspace && workspace_bytes >= risp_blocked_class_sums_workspace(N, C, H, K), RISP_E_WORKSPACE,
+               "risp_blocked_class_sums: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int CG = (C + 3) / 4;
+  class_sums_rows_kernel<<<dim3((unsigned)H, (unsigned)N), 256, 0, st>>>(g_blk, mask_blk, static_cast<float*>(workspace), CG, H, W, K);
+  class_sums_final_kernel<<<dim3((unsigned)K, (unsigned)N), 256, 0, st>>>(static_cast<const float*>(workspace), out, CG, H, K, CP);
+  return check_launch("class_sums");
+}
+
 // x, res, y_blk in the blocked layout with channel groups CinG = pad16(Cin)/4, CoutG = pad16(Cout)/4
 extern "C" int risp_conv_tc_fwd(const float* x_blk, const float* mask_in_blk, const float* wprep, const float* bias,
                                 const float* res_blk, const float* mask_out_blk, float* y_blk, float* y_planar, int N, int Cin,
                                 int Cout, int H, int W, int K, int flags, risp_stream_t stream) {
+  return risp_conv_tc_fwd_tab(x_blk, mask_in_blk, wprep, bias, nullptr, res_blk, mask_out_blk, y_blk, y_planar, N, Cin, Cout, H, W, K,
+                              flags, stream);
+}
+
+extern "C" int risp_conv_tc_fwd_tab(const float* x_blk, const float* mask_in_blk, const float* wprep, const float* bias,
+                                    const float* bias_tab, const float* res_blk, const float* mask_out_blk, float* y_blk,
+                                    float* y_planar, int N, int Cin, int Cout, int H, int W, int K, int flags, risp_stream_t stream) {
   RISP_REQUIRE(x_blk && wprep && (y_blk || y_planar) && N > 0 && H > 0 && W > 0 && N <= 65535, RISP_E_INVALID,
                "risp_conv_tc_fwd: bad arguments");
+  RISP_REQUIRE(!bias_tab || (H >= K - 1 && W >= K - 1 && aligned16(bias_tab)), RISP_E_INVALID,
+               "risp_conv_tc_fwd: a bias table needs H, W >= K-1 (disjoint border classes) and 16-byte alignment");
   RISP_REQUIRE(risp_conv_tc_supported(Cin, Cout, K), RISP_E_UNSUPPORTED, "risp_conv_tc_fwd: unsupported shape %d->%d k%d", Cin, Cout, K);
   RISP_REQUIRE(!(flags & RISP_CONV_ADD_RES) || res_blk, RISP_E_INVALID, "risp_conv_tc_fwd: ADD_RES without a residual");
   const int NP = (Cout + 15) / 16 * 16;
-  ConvTcArgs a{x_blk, wprep, bias, res_blk, mask_in_blk, mask_out_blk, y_blk, y_planar, risp_conv_tc_padded_channels(Cin) / 4, Cout, NP, H, W, flags};
+  ConvTcArgs a{x_blk, wprep, bias, bias_tab, res_blk, mask_in_blk, mask_out_blk, y_blk, y_planar, risp_conv_tc_padded_channels(Cin) / 4,
+               Cout, NP, H, W, flags, Cin, ((Cin + 15) / 16 * 16 + tc_chunk(K) - 1) / tc_chunk(K)};
   cudaStream_t st = as_stream(stream);
 #define RISP_TC(KK, RR, NN, BB, MM, AA, PP, DD) return launch_tc<KK, 8, RR, NN, BB, MM, AA, PP, DD>(a, N, st)
   // R rows per CTA: the fattest MMA has N = min(R,K)*NP <= 256; TMEM columns = 2*R*NP per CTA.  MM = 2 CTAs per SM

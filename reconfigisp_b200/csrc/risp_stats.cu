@@ -60,6 +60,38 @@ __global__ void plane_stats_final(const float* __restrict__ partial, float* __re
   if (lane == 0) { out[plane * 3] = mn; out[plane * 3 + 1] = sm * inv_hw; out[plane * 3 + 2] = mx; }
 }
 
+// first position (row-major) of the plane's minimum and maximum: where torch.min(x, dim=3) -> torch.min(.., dim=2) of
+// srcnn_res_arch.py:36-40 sends its gradient on the CPU (first occurrence among ties).  idx (planes, 2) starts at INT_MAX.
+__global__ void __launch_bounds__(kT)
+plane_argfirst_kernel(const float* __restrict__ x, const float* __restrict__ stats, int* __restrict__ idx, long long HW) {
+  const int plane = blockIdx.y;
+  const float* p = x + (long long)plane * HW;
+  const float mn = stats[plane * 3], mx = stats[plane * 3 + 2];
+  int imn = 0x7fffffff, imx = 0x7fffffff;
+  for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < HW; i += (long long)gridDim.x * kT) {
+    const float v = p[i];
+    if (v == mn && (int)i < imn) imn = (int)i;
+    if (v == mx && (int)i < imx) imx = (int)i;
+  }
+  imn = __reduce_min_sync(0xffffffffu, imn);
+  imx = __reduce_min_sync(0xffffffffu, imx);
+  if ((threadIdx.x & 31) == 0) {
+    if (imn != 0x7fffffff) atomicMin(idx + plane * 2, imn);
+    if (imx != 0x7fffffff) atomicMin(idx + plane * 2 + 1, imx);
+  }
+}
+
+// dx = g_mean / HW everywhere, + g_min at the arg-min pixel, + g_max at the arg-max pixel;  g (planes, 3) = d/d[min, mean, max]
+__global__ void __launch_bounds__(kT)
+plane_stats_bwd_kernel(const float* __restrict__ g, const int* __restrict__ idx, float* __restrict__ dx, long long HW, float inv_hw) {
+  const int plane = blockIdx.y;
+  const float gm = g[plane * 3 + 1] * inv_hw, gmn = g[plane * 3], gmx = g[plane * 3 + 2];
+  const int imn = idx[plane * 2], imx = idx[plane * 2 + 1];
+  float* p = dx + (long long)plane * HW;
+  for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < HW; i += (long long)gridDim.x * kT)
+    p[i] = gm + ((int)i == imn ? gmn : 0.f) + ((int)i == imx ? gmx : 0.f);
+}
+
 __global__ void __launch_bounds__(kT)
 loglum_kernel(const float* __restrict__ x, float* __restrict__ partial, long long HW, float scale) {
   const int n = blockIdx.y;
@@ -199,6 +231,24 @@ extern "C" int risp_plane_stats(const float* x, float* out, int planes, long lon
   plane_stats_kernel<<<dim3(B, planes), kT, 0, st>>>(x, partial, HW, vec);
   plane_stats_final<<<planes, 32, 0, st>>>(partial, out, B, (float)(1.0 / (double)HW));
   return check_launch("plane_stats");
+}
+
+// idx: (planes, 2) int32 = row-major position of the first minimum / first maximum of every plane (stats from risp_plane_stats)
+extern "C" int risp_plane_argfirst(const float* x, const float* stats, int* idx, int planes, long long HW, risp_stream_t stream) {
+  RISP_REQUIRE(x && stats && idx && planes > 0 && planes <= 65535 && HW > 0 && HW < 0x7f000000ll, RISP_E_INVALID,
+               "risp_plane_argfirst: bad arguments");          // idx starts at 0x7f7f7f7f (byte memset)
+  cudaStream_t st = as_stream(stream);
+  if (cudaMemsetAsync(idx, 0x7f, sizeof(int) * 2 * (size_t)planes, st) != cudaSuccess) { set_error("risp_plane_argfirst: memset failed"); return RISP_E_CUDA; }
+  plane_argfirst_kernel<<<dim3(stat_blocks(planes, HW), planes), kT, 0, st>>>(x, stats, idx, HW);
+  return check_launch("plane_argfirst");
+}
+
+// dx (planes, HW) = gradient of [min, mean, max] per plane: g (planes, 3), idx from risp_plane_argfirst
+extern "C" int risp_plane_stats_bwd(const float* g, const int* idx, float* dx, int planes, long long HW, risp_stream_t stream) {
+  RISP_REQUIRE(g && idx && dx && planes > 0 && planes <= 65535 && HW > 0 && HW < 0x7fffffffll, RISP_E_INVALID,
+               "risp_plane_stats_bwd: bad arguments");
+  plane_stats_bwd_kernel<<<dim3(stat_blocks(planes, HW), planes), kT, 0, as_stream(stream)>>>(g, idx, dx, HW, (float)(1.0 / (double)HW));
+  return check_launch("plane_stats_bwd");
 }
 
 extern "C" int risp_loglum_mean(const float* x, float* out, int N, long long HW, float scale, void* workspace,

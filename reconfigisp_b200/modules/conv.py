@@ -24,7 +24,7 @@ def from_blocked(xb, channels):
     return ops.from_blocked(xb, channels)
 
 
-def conv2d_blocked(xb, weight, bias=None, relu_in=False, relu_out=False, residual=None, residual_relu=False):
+def conv2d_blocked(xb, weight, bias=None, relu_in=False, relu_out=False, residual=None, residual_relu=False, bias_tab=None):
     """Same contract as `conv2d`, but input / residual / output are channel-blocked (N,H,C16/4,W,4) tensors and
     the arithmetic runs on the tcgen05 tensor cores (3-term TF32 split, fp32-accurate)."""
-    return ops.conv2d_tc(xb, weight, bias, relu_in, relu_out, residual, residual_relu)
+    return ops.conv2d_tc(xb, weight, bias, relu_in, relu_out, residual, residual_relu, bias_tab)

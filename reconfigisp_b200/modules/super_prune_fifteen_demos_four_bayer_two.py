@@ -216,7 +216,10 @@ class SuperPruneFifteenDemosFourBayerTwo(nn.Module):
                 par_tensor = None if par.nelement() == 0 else torch.sigmoid(par).repeat(N, 1)
                 jobs.append(lambda i=i, x=x, p=par_tensor: mods[i](x, p))
                 widx.append(i)
+            if jobs:
+                P.prepare_shared(x)          # blocked copy + statistics of the stage input, once, on the main stream
             ext = self._fan_out(jobs)
+            P.release_shared(x)
             w = post[widx]
             dummy = self._dummy(pars, pruned)
             if dummy is not None:

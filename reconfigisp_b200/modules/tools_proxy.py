@@ -43,25 +43,104 @@ def seeded_state_dict(module, seed):
     return OrderedDict((k, torch.randn(v.shape, generator=g) * 0.05) for k, v in module.state_dict().items())
 
 
+def shared_blocked(x):
+    """Channel-blocked copy of a stage input: the one `prepare_shared` made for all candidates of a supernet step (their
+    gradients then meet in ONE from_blocked on the way back), else a fresh one."""
+    d = getattr(x, '_risp_shared', None)
+    return d['blk'] if d is not None and d['version'] == x._version else conv.to_blocked(x)
+
+
+def shared_stats3(x):
+    """(N, 9) per-image [min | mean | max] of a BGR stage input, shared by the eight SRCNNRes proxies of a supernet step."""
+    d = getattr(x, '_risp_shared', None)
+    return d['st3'] if d is not None and d['version'] == x._version else ops.plane_stats3(x)
+
+
+def prepare_shared(x):
+    """Called by the supernet on the main stream before the candidates of a step fan out over side streams; the cache is
+    only valid inside that step's autograd graph, so `release_shared` drops it once the candidates have run."""
+    x._risp_shared = {'version': x._version, 'blk': conv.to_blocked(x), 'st3': ops.plane_stats3(x)}
+
+
+def release_shared(x):
+    if hasattr(x, '_risp_shared'):
+        del x._risp_shared
+
+
+def _frozen(*convs):
+    return not any(p.requires_grad for c in convs for p in c.parameters())
+
+
+def _derived(module, name, convs, make):
+    """Weight-derived constants (folded tables, flipped copies), cached on the module and rebuilt when a weight changes."""
+    key = tuple((p._version, p.data_ptr()) for c in convs for p in c.parameters())
+    cache = module.__dict__.setdefault('_risp_derived', {})
+    if name not in cache or cache[name][0] != key:
+        with torch.no_grad():
+            cache[name] = (key, make())
+        if torch.cuda.is_available():
+            torch.cuda.current_stream().synchronize()     # built once, then read from whichever stream the candidate runs on
+    return cache[name][1]
+
+
 class SRCNNRes(nn.Module):
     """srcnn_res_arch.py:6-53.  Input = x ++ [per-image min, mean, max of every channel] ++ params,
-    broadcast over the frame; conv9-ReLU-conv5-ReLU-conv5; global residual."""
+    broadcast over the frame; conv9-ReLU-conv5-ReLU-conv5; global residual.
+
+    The 9+P broadcast channels are never materialised when the network is frozen (the search path): a channel that is
+    constant over the frame contributes  value * (sum of the taps that fall inside the frame)  to the first convolution,
+    i.e. a per-image bias that depends only on which of the 9 x 9 border classes the output pixel is in.  That table is
+    (N, 81, 64) = features (N, 9+P) x S (9+P, 81*64) with S precomputed from the weights; the convolution itself runs on
+    the 3 image channels (1 chunk of 8 instead of 2-3), and the gradient of the features is the class-sums of the masked
+    upstream gradient times S^T (`ops.blocked_class_sums`).  The statistics and the blocked copy of x are computed once per
+    stage input and shared by the eight proxies."""
 
     def __init__(self, param_channel):
         super().__init__()
         self.srcnn = nn.Sequential(nn.Conv2d(3 + 9 + param_channel, 64, 9, 1, 4), nn.ReLU(),
                                    nn.Conv2d(64, 32, 5, 1, 2), nn.ReLU(), nn.Conv2d(32, 3, 5, 1, 2))
 
+    def _folded(self):
+        c1 = self.srcnn[0]
+
+        def make():
+            W = c1.weight.detach()
+            K, PAD = W.shape[-1], W.shape[-1] // 2
+            cls = torch.arange(K, device=W.device).view(K, 1)
+            tap = torch.arange(K, device=W.device).view(1, K)
+            # taps of an output pixel in border class a that land inside the frame (class PAD = interior: all of them)
+            M = torch.where(cls < PAD, tap >= PAD - cls, torch.where(cls == PAD, torch.ones_like(tap, dtype=torch.bool), tap <= K - cls - 1 + PAD))
+            M = M.to(torch.float64)
+            S = torch.einsum('ocyx,ay,bx->cabo', W[:, 3:].double(), M, M).reshape(W.shape[1] - 3, K * K * W.shape[0])
+            return (W[:, :3].contiguous(), S.float().contiguous(), c1.bias.detach().float().repeat(K * K).contiguous())
+        return _derived(self, 'folded', [c1], make)
+
     def forward(self, x, param_vec):
         x = x.float()
         N, _, H, W = x.shape
-        feat_min = x.amin(dim=(2, 3))
-        feat_mean = torch.mean(torch.mean(x, dim=3), dim=2)
-        feat_max = x.amax(dim=(2, 3))
+        c1, c2, c3 = self.srcnn[0], self.srcnn[2], self.srcnn[4]
+        if not _frozen(c1) or min(H, W) < 8:
+            return self._forward_materialised(x, param_vec)     # fine-tuning needs the weight gradients of all 12+P channels
+        st = shared_stats3(x)
         try:
-            feat = torch.cat([feat_min, feat_mean, feat_max, param_vec], dim=1)
+            feat = torch.cat([st, param_vec], dim=1)
         except Exception:
-            raise ValueError(feat_min.size(), None if param_vec is None else param_vec.size())
+            raise ValueError(st.size(), None if param_vec is None else param_vec.size())
+        w_img, S, b_rep = self._folded()
+        tab = torch.addmm(b_rep, feat, S)                        # (N, 81*64) bias of every border class
+        xb = shared_blocked(x)
+        h = conv.conv2d_blocked(xb, w_img, None, relu_out=True, bias_tab=tab)
+        h = conv.conv2d_blocked(h, c2.weight, c2.bias, relu_out=True)
+        h = conv.conv2d_blocked(h, c3.weight, c3.bias, residual=xb)
+        return conv.from_blocked(h, 3)
+
+    def _forward_materialised(self, x, param_vec):
+        N, _, H, W = x.shape
+        st = ops.plane_stats3(x)                                # [min | mean | max], gradient of min / max to the first extremum
+        try:
+            feat = torch.cat([st, param_vec], dim=1)
+        except Exception:
+            raise ValueError(st.size(), None if param_vec is None else param_vec.size())
         feat_in = torch.cat([x, feat.view(N, -1, 1, 1).expand(N, feat.shape[1], H, W)], dim=1)
         c1, c2, c3 = self.srcnn[0], self.srcnn[2], self.srcnn[4]
         h = conv.conv2d_blocked(conv.to_blocked(feat_in), c1.weight, c1.bias, relu_out=True)
@@ -145,7 +224,20 @@ class Path14lBgr(nn.Module):
                                               nn.ReLU(inplace=True), nn.Conv2d(64, 3, 3, 1, 1))
 
     def forward(self, x, param_vec):
-        h = x.float().flip(1)
+        seq = self.path_restore_14l
+        x = x.float()
+        if param_vec is None and _frozen(seq[0], seq[3]):
+            # frozen network (search path): the BGR<->RGB flips (:65, :84) are folded into the first layer's input channels
+            # and the last layer's output channels, and the blocked copy of x is the one the other candidates share
+            def make():
+                return (seq[0].weight.detach().flip(1).contiguous(), seq[3].weight.detach().flip(0).contiguous(),
+                        seq[3].bias.detach().flip(0).contiguous())
+            w_first, w_last, b_last = _derived(self, 'flipped', [seq[0], seq[3]], make)
+            hb = conv.conv2d_blocked(shared_blocked(x), w_first, seq[0].bias)
+            for blk in seq[1]:
+                hb = blk(hb)
+            return conv.from_blocked(conv.conv2d_blocked(hb, w_last, b_last, relu_in=True), 3)
+        h = x.flip(1)
         if param_vec is not None:
             N, _, H, W = h.shape
             h = torch.cat([h, param_vec.view(N, -1, 1, 1).expand(N, param_vec.shape[1], H, W)], dim=1)

@@ -153,6 +153,36 @@ def plane_stats(x):
     return out
 
 
+class _PlaneStats3Fn(torch.autograd.Function):
+    """(N,C,H,W) -> (N, 3C) = [min_c | mean_c | max_c] per image, the global features of SRCNNRes (srcnn_res_arch.py:36-40).
+    Backward: the mean spreads evenly; min / max send their gradient to the FIRST pixel (row-major) that attains them -- what
+    `torch.min(x, dim=3)` followed by `torch.min(.., dim=2)` does on the CPU reference."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _img(x)
+        N, C, H, W = x.shape
+        st = plane_stats(x)                                            # (N,C,3)
+        idx = torch.empty((N * C, 2), device=x.device, dtype=torch.int32)
+        L.call('risp_plane_argfirst', L.ptr(x), L.ptr(st), L.ptr(idx), N * C, H * W, L.stream())
+        ctx.save_for_backward(idx)
+        ctx.shape = (N, C, H, W)
+        return st.permute(0, 2, 1).reshape(N, 3 * C)
+
+    @staticmethod
+    def backward(ctx, g):
+        idx, = ctx.saved_tensors
+        N, C, H, W = ctx.shape
+        gp = g.reshape(N, 3, C).permute(0, 2, 1).contiguous()          # (N,C,3) like the statistics
+        dx = torch.empty((N, C, H, W), device=g.device, dtype=torch.float32)
+        L.call('risp_plane_stats_bwd', L.ptr(gp), L.ptr(idx), L.ptr(dx), N * C, H * W, L.stream())
+        return dx
+
+
+def plane_stats3(x):
+    return _PlaneStats3Fn.apply(x)
+
+
 def loglum_mean(x, scale=1.0):
     x = _img(x, 3)
     N, _, H, W = x.shape
@@ -826,6 +856,7 @@ def _tc_weights(weight, transpose_flip):
         n = L.size('risp_conv_tc_weight_floats', Cin, Cout, K, int(transpose_flip))
         wk = torch.empty((n,), device=weight.device, dtype=torch.float32)
         L.call('risp_conv_tc_prepare_weights', L.ptr(weight.detach().contiguous()), L.ptr(wk), Cin, Cout, K, int(transpose_flip), L.stream())
+        torch.cuda.current_stream().synchronize()       # prepared once, then read from whichever stream the candidate runs on
         if cache is None or any(k[1:] != key[1:] for k in cache):
             cache = {}
         cache[key] = wk
@@ -836,19 +867,30 @@ def _tc_weights(weight, transpose_flip):
     return cache[key]
 
 
-def _conv_tc_raw(xb, mask_in, wk, bias, resb, mask_out, Cin, Cout, K, flags):
+def _conv_tc_raw(xb, mask_in, wk, bias, resb, mask_out, Cin, Cout, K, flags, bias_tab=None):
     N, H, _, W, _ = xb.shape
     yb = torch.empty((N, H, tc_groups(Cout), W, 4), device=xb.device, dtype=torch.float32)
-    L.call('risp_conv_tc_fwd', L.ptr(xb), L.ptr(mask_in), L.ptr(wk), L.ptr(bias), L.ptr(resb), L.ptr(mask_out), L.ptr(yb), None,
-           N, Cin, Cout, H, W, K, int(flags), L.stream())
+    L.call('risp_conv_tc_fwd_tab', L.ptr(xb), L.ptr(mask_in), L.ptr(wk), L.ptr(bias), L.ptr(bias_tab), L.ptr(resb), L.ptr(mask_out),
+           L.ptr(yb), None, N, Cin, Cout, H, W, K, int(flags), L.stream())
     return yb
+
+
+def blocked_class_sums(gb, mask_b, C, K):
+    """(N,H,CG,W,4) blocked gradient -> (N, K*K, pad16(C)) sums over the K x K border classes of the pixels (the backward of a
+    position-class bias table, see risp_conv_tc_fwd_tab)."""
+    N, H, _, W, _ = gb.shape
+    CP = (C + 15) // 16 * 16
+    out = torch.empty((N, K * K, CP), device=gb.device, dtype=torch.float32)
+    ws = L.workspace(L.size('risp_blocked_class_sums_workspace', N, C, H, K), gb.device)
+    L.call('risp_blocked_class_sums', L.ptr(gb), L.ptr(mask_b), L.ptr(out), N, C, CP, H, W, K, L.ptr(ws), ws.numel() * 4, L.stream())
+    return out
 
 
 class _ConvTcFn(torch.autograd.Function):
     """Blocked-layout convolution on the tensor cores; same contract as `_ConvFn` (data gradients only)."""
 
     @staticmethod
-    def forward(ctx, xb, resb, weight, bias, relu_in, relu_out, res_relu):
+    def forward(ctx, xb, resb, weight, bias, relu_in, relu_out, res_relu, bias_tab=None):
         xb = xb.contiguous()
         Cout, Cin, K, _ = weight.shape
         assert xb.shape[2] == tc_groups(Cin), 'blocked input has %d groups, weight expects %d' % (xb.shape[2], tc_groups(Cin))
@@ -858,8 +900,12 @@ class _ConvTcFn(torch.autograd.Function):
             resb = resb.contiguous()
             flags |= CONV_ADD_RES | (CONV_RES_RELU if res_relu else 0)
         b = None if bias is None else bias.detach().float().contiguous()
-        yb = _conv_tc_raw(xb, None, _tc_weights(weight, False), b, resb, None, Cin, Cout, K, flags)
+        if bias_tab is not None:
+            assert bias is None and tuple(bias_tab.shape) == (xb.shape[0], K * K * ((Cout + 15) // 16 * 16)), 'bias table: (N, K*K*pad16(Cout))'
+            bias_tab = bias_tab.detach().contiguous()
+        yb = _conv_tc_raw(xb, None, _tc_weights(weight, False), b, resb, None, Cin, Cout, K, flags, bias_tab)
         ctx.cfg = (relu_in, relu_out, res_relu, Cin, Cout, K)
+        ctx.has_tab = bias_tab is not None
         ctx.save_for_backward(xb if relu_in else None, yb if relu_out else None, resb if (resb is not None and res_relu) else None, weight)
         ctx.has_res = resb is not None
         ctx.xb_full = xb if (weight.requires_grad or (bias is not None and bias.requires_grad)) else None
@@ -883,9 +929,12 @@ class _ConvTcFn(torch.autograd.Function):
             dyp = _FromBlockedFn.apply(dyb, Cout)
             yp = _FromBlockedFn.apply(yb, Cout) if relu_out else None
             dw, db = conv_weight_grads(xp, dyp, yp, weight.shape, relu_in, ctx.needs_input_grad[2], ctx.needs_input_grad[3])
-        return dxb, dres, dw, db, None, None, None
+        dtab = None
+        if ctx.has_tab and ctx.needs_input_grad[7]:
+            dtab = blocked_class_sums(dyb, yb if relu_out else None, Cout, K).view(dyb.shape[0], -1)
+        return dxb, dres, dw, db, None, None, None, dtab
 
 
-def conv2d_tc(xb, weight, bias=None, relu_in=False, relu_out=False, residual=None, residual_relu=False):
-    """Blocked in, blocked out."""
-    return _ConvTcFn.apply(xb, residual, weight, bias, relu_in, relu_out, residual_relu)
+def conv2d_tc(xb, weight, bias=None, relu_in=False, relu_out=False, residual=None, residual_relu=False, bias_tab=None):
+    """Blocked in, blocked out.  bias_tab (N, K*K*pad16(Cout)): differentiable position-class bias (instead of `bias`)."""
+    return _ConvTcFn.apply(xb, residual, weight, bias, relu_in, relu_out, residual_relu, bias_tab)

@@ -311,3 +311,75 @@ def test_tuning_fast_step_matches_autograd_step(crit):
     # state-dict keys and shapes are untouched by the flat re-layout
     sa, sb = models[0].netG.state_dict(), models[1].netG.state_dict()
     assert list(sa.keys()) == list(sb.keys()) and all(sa[k].shape == sb[k].shape for k in sa)
+
+
+# ---- SRCNNRes with its constant channels folded into a border-class bias table (search path) ---------------------------
+def _ref_stats3(x):
+    """srcnn_res_arch.py:36-40, verbatim reductions (CPU)."""
+    mn, _ = torch.min(x, dim=3)
+    mn, _ = torch.min(mn, dim=2)
+    me = torch.mean(torch.mean(x, dim=3), dim=2)
+    mx, _ = torch.max(x, dim=3)
+    mx, _ = torch.max(mx, dim=2)
+    return torch.cat([mn, me, mx], dim=1)
+
+
+def test_plane_stats3_routes_min_max_gradient_like_the_reference():
+    from reconfigisp_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(3, 3, 18, 22, generator=g).clamp(0.25, 0.75)        # many ties at both extremes
+    x[1, 2] = 0.5                                                       # a constant plane: min == max everywhere
+    w = torch.randn(3, 9, generator=g)
+    xc = x.clone().requires_grad_()
+    sc = _ref_stats3(xc)
+    gc, = torch.autograd.grad((sc * w).sum(), xc)
+    xg = x.cuda().requires_grad_()
+    sg = ops.plane_stats3(xg)
+    gg, = torch.autograd.grad((sg * w.cuda()).sum(), xg)
+    assert torch.equal(sg[:, :3].cpu(), sc[:, :3]) and torch.equal(sg[:, 6:].cpu(), sc[:, 6:])     # min / max bit-exact
+    assert maxabs(sg[:, 3:6], sc[:, 3:6].detach()) <= 1e-6
+    assert maxabs(gg, gc) <= 1e-6          # same single pixel receives the min / max gradient
+
+
+@pytest.mark.parametrize('K,C,shape', [(9, 64, (2, 20, 24)), (9, 64, (1, 8, 8)), (5, 32, (2, 11, 150)), (3, 3, (1, 6, 5))])
+def test_blocked_class_sums_match_torch(K, C, shape):
+    from reconfigisp_b200 import ops
+    N, H, W = shape
+    g = torch.Generator().manual_seed(5)
+    d = torch.randn(N, C, H, W, generator=g).cuda()
+    m = torch.randn(N, C, H, W, generator=g).cuda()
+    PAD = K // 2
+    cy = torch.tensor([y if y < PAD else (K - (H - y) if y >= H - PAD else PAD) for y in range(H)])
+    cx = torch.tensor([x if x < PAD else (K - (W - x) if x >= W - PAD else PAD) for x in range(W)])
+    oh = torch.zeros(H, W, K * K, dtype=torch.float64)
+    oh[torch.arange(H).view(H, 1), torch.arange(W).view(1, W), cy.view(H, 1) * K + cx.view(1, W)] = 1
+    for mask in (None, m):
+        dm = d if mask is None else d * (mask > 0)
+        ref = torch.einsum('nchw,hwk->nkc', dm.double().cpu(), oh)
+        out = ops.blocked_class_sums(ops.to_blocked(d), None if mask is None else ops.to_blocked(mask), C, K)
+        assert out.shape == (N, K * K, (C + 15) // 16 * 16)
+        assert maxabs(out[..., :C], ref) <= 1e-4 * max(1.0, float(ref.abs().max()))
+        assert float(out[..., C:].abs().max()) == 0.0 if out.shape[-1] > C else True
+
+
+@pytest.mark.parametrize('P_,shape', [(2, (2, 20, 24)), (1, (1, 8, 8)), (5, (2, 37, 150)), (3, (1, 64, 260))])
+def test_srcnn_res_folded_constant_channels_match_materialised(P_, shape):
+    from reconfigisp_b200.modules import tools_proxy as P
+    N, H, W = shape
+    g = torch.Generator().manual_seed(11)
+    net = P.ProxyNet(P_, None)
+    net.load_state_dict(P.seeded_state_dict(net, 20 + P_))
+    net = net.cuda()
+    x0 = torch.rand(N, 3, H, W, generator=g).clamp(0.1, 0.9).cuda()
+    p0 = torch.rand(N, P_, generator=g).cuda()
+    dy = torch.randn(N, 3, H, W, generator=g).cuda()
+    res = {}
+    for mode in ('folded', 'materialised'):
+        net.requires_grad_(mode == 'materialised')       # frozen -> folded table; trainable -> the reference's concat
+        x, p = x0.clone().requires_grad_(), p0.clone().requires_grad_()
+        y = net(x, p)
+        res[mode] = (y,) + torch.autograd.grad(y, [x, p], dy)
+    (yf, dxf, dpf), (ym, dxm, dpm) = res['folded'], res['materialised']
+    assert maxabs(yf, ym) <= 2e-5 * max(1.0, float(ym.detach().abs().max())), (maxabs(yf, ym), float(ym.detach().abs().max()))
+    relclose_relu_net(dxf, dxm, rtol=1e-4, flip_frac=2e-2)
+    relclose(dpf, dpm, rtol=2e-3, atol=1e-5)
