@@ -1,6 +1,10 @@
-// Tensor-core convolution for the CNN candidates: implicit GEMM on tcgen05 (UMMA, kind::tf32) with TMEM
-// accumulators, fp32-accurate through a 3-term split (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo; the dropped
-// a_lo*b_lo term is ~2^-21 relative), so the 1e-4 parity bar of this path holds.
+// Tensor-core convolution for the CNN candidates: implicit GEMM on tcgen05 (UMMA) with TMEM accumulators,
+// fp32-accurate through a 3-term split  a*b ~ a_hi*b_hi + (a_lo*b + a*b_lo)  (a_hi, b_hi = the TF32 truncations; the
+// dropped a_lo*b_lo term is ~2^-22 relative), so the 1e-4 parity bar of this path holds.  The main term is ONE
+// kind::tf32 MMA (K = 8 channels).  The two cross terms are ~2^-11 of the main term, so 8 mantissa bits are enough for
+// them: they are ONE kind::f16 MMA on bf16 operands whose K = 16 is [a_lo(4) | a(4)] x [b(4) ; b_lo(4)] per 4-channel
+// group -- two instructions per 8 channels instead of three, and the bf16 tile has exactly the geometry (16 bytes per
+// pixel and channel group) of the fp32 tile, so both use the same descriptors.  Error of the cross terms: 2^-9 * 2^-11.
 //
 // GEMM view: M = 128 consecutive pixels of one output row, N = output channels (16..64), K = taps x input
 // channels.  Activations live in a channel-blocked layout [N][H][C/4][W][4] so that, for a group of 4 input
@@ -15,6 +19,7 @@
 // One elected thread issues the MMAs; completion is tracked with tcgen05.commit -> mbarrier; the epilogue
 // reads TMEM with tcgen05.ld (32x32b), applies bias / ReLU / residual and writes the blocked layout (and/or
 // planar NCHW) with 128-bit stores.
+#include <cuda_bf16.h>
 #include "risp_common.cuh"
 
 namespace risp {
@@ -53,6 +58,21 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// nearest TF32 value (10 explicit mantissa bits, low 13 bits zero): the residual a - tf32_rn(a) is at most 2^-12 |a|, half of
+// what truncation leaves, which halves every error term of the bf16 cross-term MMA
+__device__ __forceinline__ float tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float lo_elem, float hi_elem) {      // lo_elem at the lower address
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
 }
 __device__ __forceinline__ void umma_commit(uint32_t mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
@@ -287,13 +307,14 @@ conv_tc_kernel(ConvTcArgs a) {
       float4 t = v[it];
       if (relu_in) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
       float4 hi, lo;
-      hi.x = __uint_as_float(__float_as_uint(t.x) & 0xffffe000u); lo.x = t.x - hi.x;
-      hi.y = __uint_as_float(__float_as_uint(t.y) & 0xffffe000u); lo.y = t.y - hi.y;
-      hi.z = __uint_as_float(__float_as_uint(t.z) & 0xffffe000u); lo.z = t.z - hi.z;
-      hi.w = __uint_as_float(__float_as_uint(t.w) & 0xffffe000u); lo.w = t.w - hi.w;
+      hi.x = tf32_rn(t.x); lo.x = t.x - hi.x;
+      hi.y = tf32_rn(t.y); lo.y = t.y - hi.y;
+      hi.z = tf32_rn(t.z); lo.z = t.z - hi.z;
+      hi.w = tf32_rn(t.w); lo.w = t.w - hi.w;
       if (i < C::A_TOTAL) {
         reinterpret_cast<float4*>(sA_hi)[i] = hi;
-        reinterpret_cast<float4*>(sA_lo)[i] = lo;
+        // cross-term operand, 8 bf16 per pixel and channel group: [a_lo(4) | a(4)]
+        reinterpret_cast<uint4*>(sA_lo)[i] = make_uint4(pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w), pack_bf16(t.x, t.y), pack_bf16(t.z, t.w));
       }
     }
   };
@@ -377,7 +398,9 @@ conv_tc_kernel(ConvTcArgs a) {
           const int r_hi = (i < R - 1) ? i : R - 1;
           const int nrows = r_hi - r_lo + 1;
           const int j0 = r_lo - (i - K + 1);
-          const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((nrows * NP) >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+          const uint32_t shape = ((uint32_t)((nrows * NP) >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+          const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | shape;       // D fp32, A/B tf32, K-major
+          const uint32_t idesc_x = (1u << 4) | (1u << 7) | (1u << 10) | shape;     // D fp32, A/B bf16, K-major
           const uint32_t d_main = tmem_base + (uint32_t)(r_lo * NP);
           const uint32_t d_cross = tmem_base + (uint32_t)((R + r_lo) * NP);
 #pragma unroll
@@ -389,8 +412,7 @@ conv_tc_kernel(ConvTcArgs a) {
             const uint64_t dBh = make_desc(sBh + b_off, C::NSTACK * 16, 128);
             const uint64_t dBl = make_desc(sBl + b_off, C::NSTACK * 16, 128);
             umma_tf32(d_main, dAh, dBh, idesc, 1u);
-            umma_tf32(d_cross, dAl, dBh, idesc, 1u);
-            umma_tf32(d_cross, dAh, dBl, idesc, 1u);
+            umma_bf16(d_cross, dAl, dBl, idesc_x, 1u);          // a_lo*b + a*b_lo in one K = 16 instruction
           }
         }
         }
@@ -486,7 +508,8 @@ conv_tc_kernel(ConvTcArgs a) {
   }
 }
 
-// weights (Cout,Cin,K,K) -> [chunk][dx][kg][j = K-1-dy][NP][4] hi block, then the lo block.
+// weights (Cout,Cin,K,K) -> [chunk][dx][kg][j = K-1-dy][NP][4] hi block (tf32 truncations), then the cross-term block of the
+// same geometry (16 bytes per element, bf16).
 // transpose_flip: data-gradient operator.
 __global__ void conv_tc_prepare_kernel(const float* __restrict__ w, float* __restrict__ out, int Cin, int Cout, int K, int CI_C,
                                        int NP, int transpose_flip, long long total) {
@@ -507,9 +530,12 @@ __global__ void conv_tc_prepare_kernel(const float* __restrict__ w, float* __res
       if (!transpose_flip) v = w[(((long long)co * Cin + ci) * K + dy) * K + dx];
       else v = w[(((long long)ci * Cin + co) * K + (K - 1 - dy)) * K + (K - 1 - dx)];
     }
-    const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    const float hi = tf32_rn(v);
     out[i] = hi;
-    out[total + i] = v - hi;
+    // cross-term operand: per (k-group, n) 8 bf16 = [b(4) ; b_lo(4)], pairing with the activations' [a_lo(4) | a(4)]
+    __nv_bfloat16* xo = reinterpret_cast<__nv_bfloat16*>(out + total) + (i / 4) * 8;
+    xo[e] = __float2bfloat16_rn(v);
+    xo[4 + e] = __float2bfloat16_rn(v - hi);
   }
 }
 
@@ -569,32 +595,55 @@ class_sums_rows_kernel(const float* __restrict__ g, const float* __restrict__ ma
   };
   for (int cg = warp; cg < CG; cg += 8) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int x = PAD + lane; x < W - PAD; x += 32) {
+    int x = PAD + lane;
+    for (; x + 96 < W - PAD; x += 128) {                                // four independent loads (eight with a mask) in flight
+      const float4 v0 = load(cg, x), v1 = load(cg, x + 32), v2 = load(cg, x + 64), v3 = load(cg, x + 96);
+      acc.x += (v0.x + v1.x) + (v2.x + v3.x); acc.y += (v0.y + v1.y) + (v2.y + v3.y);
+      acc.z += (v0.z + v1.z) + (v2.z + v3.z); acc.w += (v0.w + v1.w) + (v2.w + v3.w);
+    }
+    for (; x < W - PAD; x += 32) {
       const float4 v = load(cg, x);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
     if (lane == 0) out[PAD * CG + cg] = acc;
     if (lane < 2 * PAD) {
-      const int x = lane < PAD ? lane : W - 2 * PAD + lane;               // classes 0..PAD-1 and PAD+1..K-1
+      const int xb = lane < PAD ? lane : W - 2 * PAD + lane;              // classes 0..PAD-1 and PAD+1..K-1
       const int cls = lane < PAD ? lane : lane + 1;
-      out[cls * CG + cg] = load(cg, x);
+      out[cls * CG + cg] = load(cg, xb);
     }
   }
 }
 
-__global__ void class_sums_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int CG, int H, int K, int CP) {
-  // grid (K y-classes, N); threads over (x-class, channel)
-  const int ycls = blockIdx.x, n = blockIdx.y, PAD = K / 2, C4 = CG * 4;
-  for (int i = threadIdx.x; i < K * CP; i += blockDim.x) {
-    const int xcls = i / CP, c = i % CP;
-    float acc = 0.f;
-    if (c < C4) {
-      const int y0 = ycls < PAD ? ycls : (ycls == PAD ? PAD : H - K + ycls);
-      const int y1 = ycls == PAD ? H - PAD : y0 + 1;
-      for (int y = y0; y < y1; ++y) acc += partial[(((long long)n * H + y) * K + xcls) * C4 + c];
+// grid (K x-classes, N); 256 threads = C4 channels x (256 / C4) row lanes
+__global__ void __launch_bounds__(256)
+class_sums_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int CG, int H, int K, int CP) {
+  __shared__ float red[256];
+  const int xcls = blockIdx.x, n = blockIdx.y, PAD = K / 2, C4 = CG * 4;
+  const int nlan = 256 / C4, c = threadIdx.x % C4, rl = threadIdx.x / C4;
+  const float* base = partial + ((long long)n * H * K + xcls) * C4 + c;
+  const long long ystride = (long long)K * C4;
+  float acc = 0.f;
+  if (rl < nlan) {
+#pragma unroll 8
+    for (int y = PAD + rl; y < H - PAD; y += nlan) acc += base[y * ystride];
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (rl == 0) {
+    for (int j = 1; j < nlan; ++j) acc += red[j * C4 + c];
+    out[(((long long)n * K + PAD) * K + xcls) * CP + c] = acc;
+  }
+  if (rl < nlan) {
+    for (int j = rl; j < 2 * PAD; j += nlan) {                          // the single-row classes
+      const int ycls = j < PAD ? j : j + 1, y = j < PAD ? j : H - 2 * PAD + j;
+      out[(((long long)n * K + ycls) * K + xcls) * CP + c] = base[y * ystride];
     }
-    out[(((long long)n * K + ycls) * K + xcls) * CP + c] = acc;
+  }
+  // zero the padding channels
+  for (int i = threadIdx.x; i < K * (CP - C4); i += 256) {
+    const int ycls = i / (CP - C4), cc = C4 + i % (CP - C4);
+    out[(((long long)n * K + ycls) * K + xcls) * CP + cc] = 0.f;
   }
 }
 
@@ -673,6 +722,7 @@ extern "C" int risp_blocked_class_sums(const float* g_blk, const float* mask_blk
   cudaStream_t st = as_stream(stream);
   const int CG = (C + 3) / 4;
   class_sums_rows_kernel<<<dim3((unsigned)H, (unsigned)N), 256, 0, st>>>(g_blk, mask_blk, static_cast<float*>(workspace), CG, H, W, K);
+  RISP_REQUIRE(CG * 4 <= 256, RISP_E_UNSUPPORTED, "risp_blocked_class_sums: more than 256 channels");
   class_sums_final_kernel<<<dim3((unsigned)K, (unsigned)N), 256, 0, st>>>(static_cast<const float*>(workspace), out, CG, H, K, CP);
   return check_launch("class_sums");
 }

@@ -127,7 +127,7 @@ class SRCNNRes(nn.Module):
         except Exception:
             raise ValueError(st.size(), None if param_vec is None else param_vec.size())
         w_img, S, b_rep = self._folded()
-        tab = torch.addmm(b_rep, feat, S)                        # (N, 81*64) bias of every border class
+        tab = ops.bias_table(feat, S, b_rep)                     # (N, 81*64) bias of every border class
         xb = shared_blocked(x)
         h = conv.conv2d_blocked(xb, w_img, None, relu_out=True, bias_tab=tab)
         h = conv.conv2d_blocked(h, c2.weight, c2.bias, relu_out=True)
@@ -183,6 +183,8 @@ class ResidualBlock(nn.Module):
     def forward(self, x):
         """x and the result are channel-blocked tensors (see modules/conv.py)."""
         c1, c2 = self.basic[1], self.basic[3]
+        if _frozen(c1, c2) and c1.weight.shape[0] == c1.weight.shape[1] == c2.weight.shape[0]:
+            return ops.resblock_tc(x, c1.weight, c1.bias, c2.weight, c2.bias)     # both convs + a two-launch backward
         t = conv.conv2d_blocked(x, c1.weight, c1.bias, relu_in=True, relu_out=True)
         return conv.conv2d_blocked(t, c2.weight, c2.bias, residual=x, residual_relu=True)
 
