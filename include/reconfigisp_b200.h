@@ -316,7 +316,8 @@ int risp_conv2d_bwd_weight(const float* x, const float* dy, const float* mask_dy
  * 3-term hi/lo split so the result stays fp32-accurate (<= ~1e-6 relative), on CHANNEL-BLOCKED activations
  * (N, H, C4/4, W, 4) where C4 = channels padded to a multiple of 4 (risp_conv_tc_padded_channels).
  * risp_to_blocked / risp_from_blocked convert from / to planar NCHW.  Same flags and mask semantics as
- * risp_conv2d_fwd; the output goes to the blocked tensor and/or a planar NCHW tensor (either may be NULL). */
+ * risp_conv2d_fwd; the output goes to the blocked tensor y_blk (required) and, if y_planar is not NULL, is also copied to
+ * that planar NCHW tensor. */
 int risp_conv_tc_supported(int Cin, int Cout, int K);
 int risp_conv_tc_padded_channels(int C);
 size_t risp_conv_tc_weight_floats(int Cin, int Cout, int K, int transpose_flip);
@@ -345,6 +346,8 @@ int risp_blocked_class_sums(const float* g_blk, const float* mask_blk, float* ou
 /* Diagnostic: per-phase clock64 timeline of one CTA of the last tensor-core convolution (builds with -DRISP_TC_TRACE only;
  * zeros otherwise).  out_host: HOST long long[16]. */
 int risp_debug_tc_trace(long long* out_host);
+/* Tuning knob: selects an alternative tile configuration of risp_conv_tc_fwd where one is compiled in (0 = default). */
+int risp_debug_tc_variant(int variant);
 int risp_debug_mma_rate(long long* out, int NP, int iters, int n_acc, int split3, int a_pw, risp_stream_t stream);
 
 #ifdef __cplusplus

@@ -36,7 +36,7 @@ struct ConvTcArgs {
   const float* mask_in;  // nullable, blocked like x: x is multiplied by [mask_in > 0] while staging (backward of an output ReLU)
   const float* mask_out; // nullable, blocked like y: the result is multiplied by [mask_out > 0] (backward of an input ReLU)
   float* y_blk;          // nullable, blocked (N, H, CoutG, W, 4)
-  float* y_pln;          // nullable, planar (N, Cout, H, W)
+  float* y_pln;          // (unused by the kernel: a planar copy is a from_blocked pass after it)
   int CinG, Cout, CoutPad, H, W, flags;
   int Cin;               // real input channels: only ceil(Cin/8) chunks are multiplied (the rest of the layout is zero padding)
   int w_chunks;          // chunks the weights were prepared with (the lo block follows the hi block of ALL chunks)
@@ -442,64 +442,80 @@ conv_tc_kernel(ConvTcArgs a) {
   mbar_wait(afree + 8u * (uint32_t)((n_chunks - 1) % ABUF), (uint32_t)(((n_chunks - 1) / ABUF) & 1));
   tc_fence_after();
   TC_TRACE(3);
+#ifdef RISP_TC_TRACE
+  tacc[0] = 0;
+#endif
+  // With 8 warps per CTA (2 per scheduler) this straight-line code is bound by dependent-instruction latency, so it is kept
+  // short (~30 instructions per 16-byte store; a first version needed ~140 and took as long as the MMAs of a 9x9 layer):
+  // row base pointers are hoisted, offsets inside a row are 32-bit, the ReLU / residual-ReLU switches are clamps against
+  // 0 or -inf instead of branches, and the bias / residual / mask values of a 16-channel group are all requested before the
+  // TMEM loads are waited for.
   const bool relu_out = (a.flags & RISP_CONV_RELU_OUT) != 0, add_res = (a.flags & RISP_CONV_ADD_RES) != 0,
              res_relu = (a.flags & RISP_CONV_RES_RELU) != 0;
+  const float out_floor = relu_out ? 0.f : -INFINITY, res_floor = res_relu ? 0.f : -INFINITY;
   const int lq = warp & 3, half = warp >> 2;
   const int gx = x0 + lq * 32 + lane;
-  const int CoutG = (a.Cout + 3) / 4;                   // groups of the blocked output / residual / mask (layout: ceil(C/4))
-  const long long orow = (long long)CoutG * a.W * 4;
+  const int cout4 = (a.Cout + 3) & ~3;                  // channels of the blocked output / residual / mask (layout: ceil(C/4) groups)
+  const int gstride = a.W * 4;                          // floats between channel groups of one row
+  const int orow = (cout4 >> 2) * gstride;              // floats per row
   // border class of the output pixel (bias table): taps that fall outside the frame see zero padding, so the folded
   // contribution of a spatially constant channel depends on which of the K x K border classes the pixel is in
-  const int xcls = gx < C::PAD ? gx : (gx >= a.W - C::PAD ? K - (a.W - gx) : C::PAD);
+  const int gxc = gx < a.W ? gx : a.W - 1;              // lanes beyond the frame load (and discard) the last pixel's bias
+  const int xcls = gxc < C::PAD ? gxc : (gxc >= a.W - C::PAD ? K - (a.W - gxc) : C::PAD);
+  const long long img_base = (long long)n * a.H * orow + (long long)gx * 4;
+  const uint32_t t_lane = tmem_base + ((uint32_t)(lq * 32) << 16);
+  const bool has_mask = a.mask_out != nullptr;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int gy = y0 + r;                              // warp-uniform
+    const bool ok = gy < a.H && gx < a.W;
+    const long long rb = img_base + (long long)gy * orow;
+    float* yrow = a.y_blk + rb;
+    const float* rrow = a.res + rb;                     // only dereferenced when the pointer is set
+    const float* mrow = a.mask_out + rb;
+    const int gyc = gy < a.H ? gy : a.H - 1;
+    const int ycls = gyc < C::PAD ? gyc : (gyc >= a.H - C::PAD ? K - (a.H - gyc) : C::PAD);
+    // generic pointer: the per-class row of the bias table (global) or the staged per-channel bias (shared)
+    const float* bsrc = a.bias_tab ? a.bias_tab + ((long long)n * (K * K) + ycls * K + xcls) * a.CoutPad : s_bias;
 #pragma unroll
     for (int cb = 0; cb < NP / 16; ++cb) {
       if ((cb & 1) != half && NP > 16) continue;        // split the column groups between the two warp sets
       if (NP == 16 && half != 0) continue;
       float v[16], vc[16];
-      tmem_ld<16>(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(r * NP + cb * 16), v);
-      tmem_ld<16>(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)((R + r) * NP + cb * 16), vc);
+#ifdef RISP_TC_TRACE
+      tq = clock64();
+#endif
+      tmem_ld<16>(t_lane + (uint32_t)(r * NP + cb * 16), v);
+      tmem_ld<16>(t_lane + (uint32_t)((R + r) * NP + cb * 16), vc);
+      float4 bb[4], rr[4], mm[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int co = cb * 16 + q * 4;
+        const bool live = ok && co < cout4;
+        bb[q] = *reinterpret_cast<const float4*>(bsrc + co);
+        rr[q] = (live && add_res) ? __ldg(reinterpret_cast<const float4*>(rrow + (cb * 4 + q) * gstride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_mask) mm[q] = live ? __ldg(reinterpret_cast<const float4*>(mrow + (cb * 4 + q) * gstride)) : make_float4(1.f, 1.f, 1.f, 1.f);
+      }
       tmem_ld_wait();
+      TC_TRACE_ADD(8, tq);          // slot 8 is re-used in the epilogue: cycles in TMEM loads (thread 0)
 #pragma unroll
-      for (int q = 0; q < 16; ++q) v[q] += vc[q];
-      if (gy < a.H && gx < a.W) {
-        const int ycls = gy < C::PAD ? gy : (gy >= a.H - C::PAD ? K - (a.H - gy) : C::PAD);
-        const float* btab = a.bias_tab ? a.bias_tab + ((long long)n * K * K + ycls * K + xcls) * a.CoutPad : nullptr;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int co = cb * 16 + q * 4;
-          if (co >= CoutG * 4) continue;                 // padding groups are not part of the layout
-          float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-          {
-            const float4 bb = btab ? __ldg(reinterpret_cast<const float4*>(btab + co)) : *reinterpret_cast<const float4*>(s_bias + co);
-            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-          }
-          if (relu_out) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-          const long long ob = ((long long)n * a.H + gy) * orow + ((long long)(co / 4) * a.W + gx) * 4;
-          if (add_res) {
-            float4 rr = __ldg(reinterpret_cast<const float4*>(a.res + ob));
-            if (res_relu) { rr.x = fmaxf(rr.x, 0.f); rr.y = fmaxf(rr.y, 0.f); rr.z = fmaxf(rr.z, 0.f); rr.w = fmaxf(rr.w, 0.f); }
-            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-          }
-          if (a.mask_out) {
-            const float4 m = __ldg(reinterpret_cast<const float4*>(a.mask_out + ob));
-            o.x = m.x > 0.f ? o.x : 0.f; o.y = m.y > 0.f ? o.y : 0.f; o.z = m.z > 0.f ? o.z : 0.f; o.w = m.w > 0.f ? o.w : 0.f;
-          }
-          if (a.y_blk) *reinterpret_cast<float4*>(a.y_blk + ob) = o;
-          if (a.y_pln) {
-            const long long plane = (long long)a.H * a.W;
-            float* pp = a.y_pln + ((long long)n * a.Cout + co) * plane + (long long)gy * a.W + gx;
-            if (co < a.Cout) pp[0] = o.x;
-            if (co + 1 < a.Cout) pp[plane] = o.y;
-            if (co + 2 < a.Cout) pp[2 * plane] = o.z;
-            if (co + 3 < a.Cout) pp[3 * plane] = o.w;
-          }
+      for (int q = 0; q < 4; ++q) {
+        const int co = cb * 16 + q * 4;
+        float4 o;
+        o.x = fmaxf(v[q * 4] + vc[q * 4] + bb[q].x, out_floor) + fmaxf(rr[q].x, res_floor);
+        o.y = fmaxf(v[q * 4 + 1] + vc[q * 4 + 1] + bb[q].y, out_floor) + fmaxf(rr[q].y, res_floor);
+        o.z = fmaxf(v[q * 4 + 2] + vc[q * 4 + 2] + bb[q].z, out_floor) + fmaxf(rr[q].z, res_floor);
+        o.w = fmaxf(v[q * 4 + 3] + vc[q * 4 + 3] + bb[q].w, out_floor) + fmaxf(rr[q].w, res_floor);
+        if (has_mask) {
+          o.x = mm[q].x > 0.f ? o.x : 0.f; o.y = mm[q].y > 0.f ? o.y : 0.f; o.z = mm[q].z > 0.f ? o.z : 0.f; o.w = mm[q].w > 0.f ? o.w : 0.f;
         }
+        if (ok && co < cout4) *reinterpret_cast<float4*>(yrow + (cb * 4 + q) * gstride) = o;
       }
     }
   }
+#ifdef RISP_TC_TRACE
+  if (trace_cta && tid == 0) { g_tc_trace[15] = clock64(); g_tc_trace[7] = tacc[0]; }     // own epilogue work done; [7] = boundary waits + TMEM-load cycles
+#endif
   tc_fence_before();
   __syncthreads();
   TC_TRACE(4);
@@ -665,6 +681,10 @@ static int launch_tc(const ConvTcArgs& a, int N, cudaStream_t st) {
 }
 
 static int tc_chunk(int K) { (void)K; return 8; }
+static int g_tc_variant = 0;        // tuning knob (risp_debug_tc_variant): alternative tile configurations of the same kernel
+}  // namespace risp
+static int conv_tc_dispatch(const risp::ConvTcArgs& a, int N, int K, int NP, cudaStream_t st);
+namespace risp {
 
 }  // namespace risp
 
@@ -738,8 +758,8 @@ extern "C" int risp_conv_tc_fwd(const float* x_blk, const float* mask_in_blk, co
 extern "C" int risp_conv_tc_fwd_tab(const float* x_blk, const float* mask_in_blk, const float* wprep, const float* bias,
                                     const float* bias_tab, const float* res_blk, const float* mask_out_blk, float* y_blk,
                                     float* y_planar, int N, int Cin, int Cout, int H, int W, int K, int flags, risp_stream_t stream) {
-  RISP_REQUIRE(x_blk && wprep && (y_blk || y_planar) && N > 0 && H > 0 && W > 0 && N <= 65535, RISP_E_INVALID,
-               "risp_conv_tc_fwd: bad arguments");
+  RISP_REQUIRE(x_blk && wprep && y_blk && N > 0 && H > 0 && W > 0 && N <= 65535, RISP_E_INVALID,
+               "risp_conv_tc_fwd: bad arguments (the blocked output is required; the planar one is an optional copy)");
   RISP_REQUIRE(!bias_tab || (H >= K - 1 && W >= K - 1 && aligned16(bias_tab)), RISP_E_INVALID,
                "risp_conv_tc_fwd: a bias table needs H, W >= K-1 (disjoint border classes) and 16-byte alignment");
   RISP_REQUIRE(risp_conv_tc_supported(Cin, Cout, K), RISP_E_UNSUPPORTED, "risp_conv_tc_fwd: unsupported shape %d->%d k%d", Cin, Cout, K);
@@ -748,6 +768,12 @@ extern "C" int risp_conv_tc_fwd_tab(const float* x_blk, const float* mask_in_blk
   ConvTcArgs a{x_blk, wprep, bias, bias_tab, res_blk, mask_in_blk, mask_out_blk, y_blk, y_planar, risp_conv_tc_padded_channels(Cin) / 4,
                Cout, NP, H, W, flags, Cin, ((Cin + 15) / 16 * 16 + tc_chunk(K) - 1) / tc_chunk(K)};
   cudaStream_t st = as_stream(stream);
+  const int rc = conv_tc_dispatch(a, N, K, NP, st);
+  if (rc != RISP_OK || !y_planar) return rc;
+  return risp_from_blocked(y_blk, y_planar, N, Cout, (Cout + 3) / 4, H, W, stream);      // optional planar copy of the result
+}
+
+static int conv_tc_dispatch(const ConvTcArgs& a, int N, int K, int NP, cudaStream_t st) {
 #define RISP_TC(KK, RR, NN, BB, MM, AA, PP, DD) return launch_tc<KK, 8, RR, NN, BB, MM, AA, PP, DD>(a, N, st)
   // R rows per CTA: the fattest MMA has N = min(R,K)*NP <= 256; TMEM columns = 2*R*NP per CTA.  MM = 2 CTAs per SM
   // where 2*R*NP <= 256 and shared memory <= 112.5 KB, otherwise one CTA with more rows.  BB = weight-stage ring depth,
@@ -756,6 +782,8 @@ extern "C" int risp_conv_tc_fwd_tab(const float* x_blk, const float* mask_in_blk
     case 1:
       switch (NP) { case 16: RISP_TC(1, 8, 16, 4, 2, 1, 1, 1); case 32: RISP_TC(1, 4, 32, 4, 2, 2, 2, 1); case 48: RISP_TC(1, 2, 48, 4, 2, 2, 2, 1); default: RISP_TC(1, 2, 64, 4, 2, 2, 2, 1); }
     case 3:
+      if (NP == 64 && g_tc_variant == 1) RISP_TC(3, 4, 64, 2, 1, 2, 2, 3);
+      if (NP == 64 && g_tc_variant == 2) RISP_TC(3, 4, 64, 4, 1, 2, 1, 1);
       switch (NP) { case 16: RISP_TC(3, 8, 16, 2, 2, 1, 1, 3); case 32: RISP_TC(3, 4, 32, 2, 2, 1, 2, 3); case 48: RISP_TC(3, 2, 48, 2, 2, 1, 2, 3); default: RISP_TC(3, 2, 64, 2, 2, 1, 2, 3); }
     case 5:
       switch (NP) { case 16: RISP_TC(5, 4, 16, 4, 2, 1, 1, 1); case 32: RISP_TC(5, 4, 32, 4, 2, 1, 1, 1); case 48: RISP_TC(5, 2, 48, 2, 2, 1, 1, 1); default: RISP_TC(5, 2, 64, 2, 2, 1, 1, 1); }
@@ -764,6 +792,8 @@ extern "C" int risp_conv_tc_fwd_tab(const float* x_blk, const float* mask_in_blk
   }
 #undef RISP_TC
 }
+
+extern "C" int risp_debug_tc_variant(int variant) { risp::g_tc_variant = variant; return RISP_OK; }
 
 // Timeline of the traced CTA of the last conv_tc launch (only meaningful in a -DRISP_TC_TRACE build): out = HOST
 // long long[16]: [0..4] clock64 at start / prologue done / all stages issued / MMAs done / end, [8] cycles waiting at
