@@ -85,9 +85,15 @@ def _load():
 lib = _load()
 
 
+_FN = {}
+
+
 def call(name, *args):
     """Invoke an `int risp_*` entry point, mapping error codes to the reference's exception types."""
-    rc = getattr(lib, name)(*args)
+    fn = _FN.get(name)
+    if fn is None:
+        fn = _FN[name] = getattr(lib, name)
+    rc = fn(*args)
     if rc != RISP_OK:
         msg = lib.risp_last_error().decode()
         raise _EXC.get(rc, RispError)('%s failed (%d): %s' % (name, rc, msg))
@@ -95,6 +101,12 @@ def call(name, *args):
 
 def size(name, *args):
     return int(getattr(lib, name)(*args))
+
+
+# The launch path is host-bound at small batches (a search iteration enqueues ~4.5 k kernels), so the per-argument checks use
+# the raw C accessors: torch.cuda.current_device() / current_stream() go through several Python layers (~1.3 / ~15 us a call).
+_cur_device = getattr(torch._C, '_cuda_getDevice', None) or torch.cuda.current_device
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
 
 
 def ptr(t):
@@ -105,15 +117,17 @@ def ptr(t):
         raise RuntimeError('reconfigisp_b200 ops run on CUDA tensors only (no CPU fallback); got a %s tensor' % t.device)
     if not t.is_contiguous():
         raise ValueError('reconfigisp_b200 ops need contiguous tensors')
-    if t.device.index != torch.cuda.current_device():
+    if t.get_device() != _cur_device():
         # kernels are enqueued on the CURRENT device's stream: a tensor of another GPU would be an illegal access
         raise RuntimeError('tensor lives on cuda:%d but the current device is cuda:%d; wrap the call in torch.cuda.device(t.device)'
-                           % (t.device.index, torch.cuda.current_device()))
-    return ctypes.c_void_p(t.data_ptr())
+                           % (t.get_device(), _cur_device()))
+    return t.data_ptr()
 
 
 def stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if _raw_stream is not None:
+        return _raw_stream(_cur_device())
+    return torch.cuda.current_stream().cuda_stream
 
 
 def iarr(values):

@@ -68,12 +68,15 @@ def release_shared(x):
 
 
 def _frozen(*convs):
-    return not any(p.requires_grad for c in convs for p in c.parameters())
+    for c in convs:
+        if c.weight.requires_grad or (c.bias is not None and c.bias.requires_grad):
+            return False
+    return True
 
 
 def _derived(module, name, convs, make):
     """Weight-derived constants (folded tables, flipped copies), cached on the module and rebuilt when a weight changes."""
-    key = tuple((p._version, p.data_ptr()) for c in convs for p in c.parameters())
+    key = tuple((c.weight._version, c.weight.data_ptr(), None if c.bias is None else c.bias._version) for c in convs)
     cache = module.__dict__.setdefault('_risp_derived', {})
     if name not in cache or cache[name][0] != key:
         with torch.no_grad():

@@ -810,8 +810,8 @@ def conv2d(x, weight, bias=None, relu_in=False, relu_out=False, residual=None, r
 
 # ---- tensor-core convolution on channel-blocked activations (csrc/risp_conv_tc.cu) ------------------------
 def tc_groups(C):
-    """number of 4-channel groups of the blocked layout (channels padded to a multiple of 16)."""
-    return L.size('risp_conv_tc_padded_channels', C) // 4
+    """number of 4-channel groups of the blocked layout = risp_conv_tc_padded_channels(C) / 4 (restated: launch-path hot spot)."""
+    return (C + 3) // 4
 
 
 class _ToBlockedFn(torch.autograd.Function):

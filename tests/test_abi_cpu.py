@@ -139,3 +139,10 @@ def test_header_is_plain_c_and_a_c_host_links():
             assert r.returncode == 0, (r.stdout, r.stderr)           # null pointers are rejected with an error code
             ver, tc, ws = r.stdout.split()
             assert int(ver) >= 1 and int(tc) == 1 and int(ws) > 0
+
+
+def test_blocked_layout_group_count_matches_the_library():
+    """ops.tc_groups restates risp_conv_tc_padded_channels (host-only entry) on the launch path."""
+    from reconfigisp_b200 import _lib as L, ops
+    for C in (1, 3, 4, 5, 12, 13, 17, 32, 48, 64):
+        assert ops.tc_groups(C) * 4 == L.size('risp_conv_tc_padded_channels', C)
