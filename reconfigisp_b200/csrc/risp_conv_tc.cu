@@ -387,9 +387,16 @@ conv_tc_kernel(ConvTcArgs a) {
         tc_fence_after();
         const uint32_t sBh = smem_u32(sB) + b * 2u * kStageBytes, sBl = sBh + kStageBytes;
         const uint32_t sAh = smem_u32(sA) + (uint32_t)(c % ABUF) * (uint32_t)(2 * C::A_FLOATS * 4), sAl = sAh + (uint32_t)(C::A_FLOATS * 4);
+        // One descriptor per operand tile and stage; every MMA's descriptor is that base plus a COMPILE-TIME offset in the
+        // start-address field (16-byte units; shared memory < 256 KB, so the 14-bit field never carries).  Building each
+        // descriptor from its address cost ~30 uniform-datapath instructions per MMA -- as long as the MMA itself runs.
+        const uint64_t dAh0 = make_desc(sAh + (uint32_t)(dx * DXS * 16), C::PW * 16, 128);
+        const uint64_t dAl0 = make_desc(sAl + (uint32_t)(dx * DXS * 16), C::PW * 16, 128);
+        const uint64_t dBh0 = make_desc(sBh, C::NSTACK * 16, 128);
+        const uint64_t dBl0 = make_desc(sBl, C::NSTACK * 16, 128);
 #pragma unroll
         for (int dxl = 0; dxl < DXS; ++dxl) {
-        const uint32_t a_dx = (uint32_t)((dx * DXS + dxl) * 16);
+        const uint32_t a_dx = (uint32_t)(dxl * 16);
         const uint32_t b_tap = (uint32_t)(dxl * C::B_TAP_FLOATS * 4);
 #pragma unroll
         for (int i = 0; i < C::ROWS; ++i) {
@@ -407,12 +414,9 @@ conv_tc_kernel(ConvTcArgs a) {
           for (int ks = 0; ks < C::KG / 2; ++ks) {
             const uint32_t a_off = (uint32_t)(i * C::A_ROW_FLOATS * 4 + (2 * ks) * C::PW * 16) + a_dx;
             const uint32_t b_off = b_tap + (uint32_t)((2 * ks) * C::NSTACK * 16 + j0 * NP * 16);
-            const uint64_t dAh = make_desc(sAh + a_off, C::PW * 16, 128);
-            const uint64_t dAl = make_desc(sAl + a_off, C::PW * 16, 128);
-            const uint64_t dBh = make_desc(sBh + b_off, C::NSTACK * 16, 128);
-            const uint64_t dBl = make_desc(sBl + b_off, C::NSTACK * 16, 128);
-            umma_tf32(d_main, dAh, dBh, idesc, 1u);
-            umma_bf16(d_cross, dAl, dBl, idesc_x, 1u);          // a_lo*b + a*b_lo in one K = 16 instruction
+            const uint64_t a16 = (uint64_t)(a_off >> 4), b16 = (uint64_t)(b_off >> 4);
+            umma_tf32(d_main, dAh0 + a16, dBh0 + b16, idesc, 1u);
+            umma_bf16(d_cross, dAl0 + a16, dBl0 + b16, idesc_x, 1u);          // a_lo*b + a*b_lo in one K = 16 instruction
           }
         }
         }
@@ -782,9 +786,12 @@ static int conv_tc_dispatch(const ConvTcArgs& a, int N, int K, int NP, cudaStrea
     case 1:
       switch (NP) { case 16: RISP_TC(1, 8, 16, 4, 2, 1, 1, 1); case 32: RISP_TC(1, 4, 32, 4, 2, 2, 2, 1); case 48: RISP_TC(1, 2, 48, 4, 2, 2, 2, 1); default: RISP_TC(1, 2, 64, 4, 2, 2, 2, 1); }
     case 3:
+      // 64 -> 64 (the Path-Restore body), measured at 64 x 256^2 (scripts/probe_tc_variants.py): one weight stage per chunk with
+      // a single input buffer 1262 us; one tap per stage + double-buffered inputs (still two CTAs per SM) 1228 us; four rows per
+      // CTA with one resident CTA 1500 us
       if (NP == 64 && g_tc_variant == 1) RISP_TC(3, 4, 64, 2, 1, 2, 2, 3);
-      if (NP == 64 && g_tc_variant == 2) RISP_TC(3, 4, 64, 4, 1, 2, 1, 1);
-      switch (NP) { case 16: RISP_TC(3, 8, 16, 2, 2, 1, 1, 3); case 32: RISP_TC(3, 4, 32, 2, 2, 1, 2, 3); case 48: RISP_TC(3, 2, 48, 2, 2, 1, 2, 3); default: RISP_TC(3, 2, 64, 2, 2, 1, 2, 3); }
+      if (NP == 64 && g_tc_variant == 2) RISP_TC(3, 2, 64, 2, 2, 1, 2, 3);
+      switch (NP) { case 16: RISP_TC(3, 8, 16, 2, 2, 1, 1, 3); case 32: RISP_TC(3, 4, 32, 2, 2, 1, 2, 3); case 48: RISP_TC(3, 2, 48, 2, 2, 1, 2, 3); default: RISP_TC(3, 2, 64, 3, 2, 2, 1, 1); }
     case 5:
       switch (NP) { case 16: RISP_TC(5, 4, 16, 4, 2, 1, 1, 1); case 32: RISP_TC(5, 4, 32, 4, 2, 1, 1, 1); case 48: RISP_TC(5, 2, 48, 2, 2, 1, 1, 1); default: RISP_TC(5, 2, 64, 2, 2, 1, 1, 1); }
     default:
