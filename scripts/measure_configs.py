@@ -107,7 +107,7 @@ def main():
 
         def it():
             m.optimize_alphas(); m.optimize_parameters()
-        ms = timeit(it, iters=iters, warm=1)
+        ms = timeit(it, iters=iters, warm=3)      # the side streams' allocator pools settle in the first iterations
         # 9.05 MFLOP/px fwd for the CNN candidates; fwd + data-gradient ~ 2x; 5 passes
         tf = 5 * 2 * 9.05e6 * N * 256 * 256 / (ms / 1e3) / 1e12
         res['cfg3_search_iter_N%d' % N] = dict(ms=round(ms, 1), iters_per_s=round(1e3 / ms, 3), MPps_per_pass=round(5 * N * 65536 / ms / 1e3, 2),
