@@ -127,6 +127,10 @@ class _Universal(nn.Module):
         super()._apply(fn, *a, **k)
         for m in self.all_modules:
             m._apply(fn, *a, **k)
+        registered = {id(p) for p in self.parameters()}
+        for p in self.all_params:                      # the empty placeholders of parameter-free stages follow the module
+            if id(p) not in registered:
+                p.data = fn(p.data)
         return self
 
     # -- reference semantics, stage by stage (isp_universal.py:210-232) --------------------------------------

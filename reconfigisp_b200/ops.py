@@ -713,6 +713,20 @@ def patch2whole(tiles, frame_hw, stride, clip01=False):
 # ---- dense convolution of the CNN candidates -------------------------------------------------------------
 CONV_RELU_IN, CONV_RELU_OUT, CONV_ADD_RES, CONV_RES_RELU = (L.ENUMS['RISP_CONV_RELU_IN'], L.ENUMS['RISP_CONV_RELU_OUT'],
                                                            L.ENUMS['RISP_CONV_ADD_RES'], L.ENUMS['RISP_CONV_RES_RELU'])
+def invalidate_weight_cache(module_or_tensor):
+    """Drop the prepared (kernel-layout) copies of convolution weights.  The caches are keyed by the tensor's version counter,
+    which in-place updates through `weight.data` (old-style checkpoint loaders, EMA code) do NOT bump: call this after such
+    an update -- `load_state_dict`, optimizers and every ordinary in-place op are tracked and need nothing."""
+    tensors = [module_or_tensor] if isinstance(module_or_tensor, torch.Tensor) else list(module_or_tensor.parameters())
+    for t in tensors:
+        for attr in ('_risp_wk', '_risp_wtc'):
+            if hasattr(t, attr):
+                delattr(t, attr)
+    if not isinstance(module_or_tensor, torch.Tensor):
+        for m in module_or_tensor.modules():
+            m.__dict__.pop('_risp_derived', None)
+
+
 def _prepared_weights(weight, transpose_flip):
     """(Cout,Cin,K,K) -> kernel layout.  Cached ON the weight tensor object (so the cache dies with it; a
     pointer-keyed cache would alias once the allocator reuses the address) and keyed by its version counter."""
@@ -758,14 +772,14 @@ class _ConvFn(torch.autograd.Function):
         b = None if bias is None else bias.detach().float().contiguous()
         y = _conv_raw(x, None, _prepared_weights(weight, False), b, res, None, Cout, K, flags)
         ctx.cfg = (relu_in, relu_out, res_relu, Cin, K)
-        ctx.save_for_backward(x if relu_in else None, y if relu_out else None, res if (res is not None and res_relu) else None, weight)
+        x_full = x if (weight.requires_grad or (bias is not None and bias.requires_grad)) else None
+        ctx.save_for_backward(x if relu_in else None, y if relu_out else None, res if (res is not None and res_relu) else None, weight, x_full)
         ctx.has_res = res is not None
-        ctx.x_full = x if (weight.requires_grad or (bias is not None and bias.requires_grad)) else None
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y, res, weight = ctx.saved_tensors
+        x, y, res, weight, x_full = ctx.saved_tensors
         relu_in, relu_out, res_relu, Cin, K = ctx.cfg
         dy = dy.contiguous()
         dx = dres = None
@@ -777,7 +791,7 @@ class _ConvFn(torch.autograd.Function):
             dres = dy if not res_relu else dy * (res > 0).to(dy.dtype)
         dw = db = None
         if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
-            dw, db = conv_weight_grads(ctx.x_full, dy, y if relu_out else None, weight.shape, relu_in,
+            dw, db = conv_weight_grads(x_full, dy, y if relu_out else None, weight.shape, relu_in,
                                        ctx.needs_input_grad[2], ctx.needs_input_grad[3])
         return dx, dres, dw, db, None, None, None
 
@@ -906,14 +920,14 @@ class _ConvTcFn(torch.autograd.Function):
         yb = _conv_tc_raw(xb, None, _tc_weights(weight, False), b, resb, None, Cin, Cout, K, flags, bias_tab)
         ctx.cfg = (relu_in, relu_out, res_relu, Cin, Cout, K)
         ctx.has_tab = bias_tab is not None
-        ctx.save_for_backward(xb if relu_in else None, yb if relu_out else None, resb if (resb is not None and res_relu) else None, weight)
+        xb_full = xb if (weight.requires_grad or (bias is not None and bias.requires_grad)) else None
+        ctx.save_for_backward(xb if relu_in else None, yb if relu_out else None, resb if (resb is not None and res_relu) else None, weight, xb_full)
         ctx.has_res = resb is not None
-        ctx.xb_full = xb if (weight.requires_grad or (bias is not None and bias.requires_grad)) else None
         return yb
 
     @staticmethod
     def backward(ctx, dyb):
-        xb, yb, resb, weight = ctx.saved_tensors
+        xb, yb, resb, weight, xb_full = ctx.saved_tensors
         relu_in, relu_out, res_relu, Cin, Cout, K = ctx.cfg
         dyb = dyb.contiguous()
         dxb = dres = None
@@ -925,7 +939,7 @@ class _ConvTcFn(torch.autograd.Function):
         dw = db = None
         if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
             # fine-tuning path only: the weight-gradient kernel works on planar tensors
-            xp = _FromBlockedFn.apply(ctx.xb_full, Cin)
+            xp = _FromBlockedFn.apply(xb_full, Cin)
             dyp = _FromBlockedFn.apply(dyb, Cout)
             yp = _FromBlockedFn.apply(yb, Cout) if relu_out else None
             dw, db = conv_weight_grads(xp, dyp, yp, weight.shape, relu_in, ctx.needs_input_grad[2], ctx.needs_input_grad[3])

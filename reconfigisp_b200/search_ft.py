@@ -28,6 +28,7 @@ class DartsFtModel(DartsModel):
         super().__init__(opt)
         ft = opt['proxy_ft_params']
         self.memory_size = ft['memory_size']
+        self.memory_bytes = int(ft.get('memory_bytes', 16 << 30))      # device FIFO cap (default 16 GiB of the 180 GB)
         self.ft_steps = ft['ft_steps']
         self.ft_data = []
         t = opt['train']
@@ -50,6 +51,11 @@ class DartsFtModel(DartsModel):
         self.ft_data.extend(t.detach().clone() for t in self.netG.intermediate_results if t.shape[1] == 3)
         if len(self.ft_data) > self.memory_size:
             self.ft_data = self.ft_data[len(self.ft_data) - self.memory_size:]
+        # the reference keeps this FIFO on the host; here it lives in HBM, so it is also capped by bytes (oldest first)
+        cap = self.memory_bytes
+        total = sum(t.numel() * 4 for t in self.ft_data)
+        while len(self.ft_data) > 1 and total > cap:
+            total -= self.ft_data.pop(0).numel() * 4
 
     def _module_grads(self, loss, params):
         return D.allreduce_mean_flat(torch.autograd.grad(loss, params, allow_unused=True))

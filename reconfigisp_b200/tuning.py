@@ -190,7 +190,9 @@ class IspModel:
         loss, dtable = step(self.img, self.gt, f['table'])
         L.call('risp_param_table_bwd', L.ptr(f['logits']), L.ptr(f['a']), L.ptr(dtable), L.ptr(f['grad']), P, L.stream())
         self.l_pix = loss.view(())
-        self.log_dict['loss'] = self.l_pix             # device scalar; `.item()` it when logging
+        # device scalar living in the step's persistent buffer: the NEXT step overwrites it, so read (`.item()`) or clone it
+        # before stepping again -- the reference stores `l_pix.item()` (isp_model.py:141)
+        self.log_dict['loss'] = self.l_pix
         return True
 
     def _fused_loss(self):
