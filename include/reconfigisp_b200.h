@@ -350,6 +350,22 @@ int risp_debug_tc_trace(long long* out_host);
 int risp_debug_tc_variant(int variant);
 int risp_debug_mma_rate(long long* out, int NP, int iters, int n_acc, int split3, int a_pw, risp_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Gradient exchange over NVLink peer memory (the all-reduce of module-parameter and architecture-weight gradients:
+ * DDP in darts_model.py:31,173; 37 .. 216 floats per backward pass).  Every rank allocates a small buffer with
+ * risp_p2p_alloc, the 64-byte IPC handles are exchanged by the host (any transport), peers map them with
+ * risp_p2p_open, and risp_p2p_allreduce_mean averages a vector in place: peer stores + epoch flags + a rank-ordered sum
+ * in one single-CTA kernel (bit-identical on every rank, CUDA-graph capturable, bounded wait).
+ * ------------------------------------------------------------------------------------- */
+size_t risp_p2p_buffer_bytes(int world, int cap);
+int risp_p2p_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+int risp_p2p_open(const unsigned char* handle64, void** peer_ptr);
+int risp_p2p_close(void* peer_ptr);
+int risp_p2p_free(void* ptr);
+int risp_p2p_timeouts(const void* buffer, int world, int cap, unsigned* out_host);
+int risp_p2p_allreduce_mean(float* data, int n, void* const* bases, int rank, int world, int cap, int timeout_ms,
+                            risp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,6 +60,69 @@ def allreduce_mean_(flat):
     return flat
 
 
+class P2PAllReduce:
+    """In-place average of a small contiguous fp32 gradient buffer across the ranks of ONE node through NVLink peer memory
+    (`csrc/risp_p2p.cu`): one single-CTA kernel instead of an NCCL collective -- ~3 us instead of ~15 us on a 0.36 ms step,
+    bit-identical on every rank, and capturable in a CUDA graph.  `P2PAllReduce.create()` returns None when it cannot be set
+    up on EVERY rank (more than 8 ranks, several nodes, IPC refused): callers then keep the NCCL path."""
+    TIMEOUT_MS = 30000
+
+    def __init__(self, cap, ptr, bases, rank, world):
+        self.cap, self.ptr, self.bases, self.rank, self.world = cap, ptr, bases, rank, world
+        from . import _lib as L
+        import ctypes
+        self._L, self._arr = L, (ctypes.c_void_p * world)(*bases)
+
+    @classmethod
+    def create(cls, cap=1024):
+        if not is_dist() or dist.get_backend() != 'nccl' or dist.get_world_size() > 8 or os.environ.get('RISP_NO_P2P'):
+            return None
+        import ctypes
+        from . import _lib as L
+        rank, world = dist.get_rank(), dist.get_world_size()
+        dev = torch.device('cuda', torch.cuda.current_device())
+        ok, ptr, bases = 1, ctypes.c_void_p(), []
+        handle = (ctypes.c_ubyte * 64)()
+        try:
+            if int(os.environ.get('LOCAL_WORLD_SIZE', world)) != world:
+                raise RuntimeError('ranks span several nodes')
+            L.call('risp_p2p_alloc', L.size('risp_p2p_buffer_bytes', world, cap), ctypes.byref(ptr), handle)
+        except Exception:
+            ok = 0
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        if ok:
+            try:
+                for r in range(world):
+                    if r == rank:
+                        bases.append(ptr.value)
+                    else:
+                        peer = ctypes.c_void_p()
+                        hb = (ctypes.c_ubyte * 64)(*allh[r].cpu().tolist())
+                        L.call('risp_p2p_open', hb, ctypes.byref(peer))
+                        bases.append(peer.value)
+            except Exception:
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)               # all ranks or none (also orders the mappings before first use)
+        if int(flag.item()) != 1:
+            return None
+        return cls(cap, ptr.value, bases, rank, world)
+
+    def __call__(self, flat):
+        assert flat.is_cuda and flat.dtype == torch.float32 and flat.is_contiguous() and flat.numel() <= self.cap
+        L = self._L
+        L.call('risp_p2p_allreduce_mean', L.ptr(flat), flat.numel(), self._arr, self.rank, self.world, self.cap, self.TIMEOUT_MS, L.stream())
+        return flat
+
+    def timeouts(self):
+        import ctypes
+        out = ctypes.c_uint(0)
+        self._L.call('risp_p2p_timeouts', self.ptr, self.world, self.cap, ctypes.byref(out))
+        return int(out.value)
+
+
 def bind_to_gpu_numa_node(local_rank):
     """Pin this process to the CPUs of the NUMA node its GPU hangs off BEFORE it allocates pinned host buffers, so that
     the H2D copies of 8 ranks do not all stream out of one socket's DRAM (e2e scaling).  Best effort: returns the node or None."""

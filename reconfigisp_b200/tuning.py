@@ -244,7 +244,8 @@ class IspModel:
         try:
             torch.cuda.synchronize()
             g_loss, g_update = torch.cuda.CUDAGraph(), None
-            if not D.is_dist():
+            if not D.is_dist() or self.__dict__.get('_p2p') is not None:
+                # single GPU, or data parallel with the peer-memory exchange (a plain kernel): the whole step is ONE graph
                 with torch.cuda.graph(g_loss):
                     self._step_eager(count=False)
             else:
@@ -280,7 +281,13 @@ class IspModel:
         self.log_dict['loss'] = self.l_pix             # device scalar; `.item()` it when logging
 
     def _allreduce_grads(self):
-        if D.is_dist():
+        if not D.is_dist():
+            return
+        if '_p2p' not in self.__dict__:                    # first exchange: try to set up the NVLink peer-memory path (all ranks or none)
+            self._p2p = D.P2PAllReduce.create(cap=max(1024, self._flat_grad.numel())) if self.opt.get('p2p_allreduce', True) else None
+        if self._p2p is not None:
+            self._p2p(self._flat_grad)                     # one single-CTA kernel: peer stores + flags + rank-ordered sum
+        else:
             D.allreduce_mean_(self._flat_grad)
 
     def _step_eager(self, count=True):

@@ -31,6 +31,23 @@ flat = torch.cat([p.detach().reshape(-1) for p in m.netG.trainable_parameters if
 both = [torch.empty_like(flat) for _ in range(world)]
 dist.all_gather(both, flat)
 assert all(torch.equal(both[0], b) for b in both), 'ranks diverged'
+# the gradient exchange ran over NVLink peer memory (csrc/risp_p2p.cu), not NCCL: hold it to NCCL on random vectors,
+# many epochs in a row (parity double-buffering), different lengths, bit-identical across ranks
+p2p = m.__dict__.get('_p2p')
+assert p2p is not None, 'peer-memory all-reduce was not set up'
+g = torch.Generator(device='cuda').manual_seed(100 + rank)
+for it in range(64):
+    n = 1 + (it * 37) % 1000
+    x = torch.randn(n, device='cuda', generator=g)
+    ref = x.clone()
+    dist.all_reduce(ref, op=dist.ReduceOp.SUM)
+    ref /= world
+    p2p(x)
+    assert float((x - ref).abs().max()) <= 1e-6, (it, float((x - ref).abs().max()))
+    allx = [torch.empty_like(x) for _ in range(world)]
+    dist.all_gather(allx, x)
+    assert all(torch.equal(allx[0], t) for t in allx), 'p2p averages differ between ranks'
+assert p2p.timeouts() == 0
 if rank == 0:
     # single-process reference on the full batch: averaging per-rank mean-gradients == full-batch gradient
     torch.save(flat.cpu(), os.environ['RISP_OUT'])
