@@ -135,6 +135,20 @@ mixed_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long H
   for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < nvec; i += (long long)gridDim.x * kT) {
     Px<NPX> X, Y;
     mix_load<VEC>(X, x + img, HW, i, C);
+    // the first batch of materialised candidates is requested BEFORE the classical candidates are evaluated, so its round trip
+    // hides behind their arithmetic (the loads are `asm volatile`: they stay where they are written)
+    float4 E[kExtBatchFwd][3];
+    auto issue_batch = [&](int e0) {
+#pragma unroll
+      for (int u = 0; u < kExtBatchFwd; ++u) {
+        const int e = e0 + u;
+        const bool live = (e < RISP_MAX_BRANCHES) && (e < d.K_ext) && !(wext[e < RISP_MAX_BRANCHES ? e : 0] < 1e-9f);
+        const float* p = d.ext[e < RISP_MAX_BRANCHES ? e : 0] + img + 4 * i;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) E[u][c] = ld_stream4_if(p + c * HW, live && c < C);
+      }
+    };
+    if (VEC == 4 && d.K_ext > 0) issue_batch(0);
 #pragma unroll
     for (int k = 0; k < NPX; ++k) { Y.b[k] = 0.f; Y.g[k] = 0.f; Y.r[k] = 0.f; }
 #pragma unroll
@@ -152,15 +166,7 @@ mixed_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long H
 #pragma unroll
       for (int e0 = 0; e0 < RISP_MAX_BRANCHES; e0 += kExtBatchFwd) {
         if (e0 < d.K_ext) {                                   // uniform
-          float4 E[kExtBatchFwd][3];
-#pragma unroll
-          for (int u = 0; u < kExtBatchFwd; ++u) {
-            const int e = e0 + u;
-            const bool live = (e < RISP_MAX_BRANCHES) && (e < d.K_ext) && !(wext[e < RISP_MAX_BRANCHES ? e : 0] < 1e-9f);
-            const float* p = d.ext[e < RISP_MAX_BRANCHES ? e : 0] + img + 4 * i;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) E[u][c] = ld_stream4_if(p + c * HW, live && c < C);
-          }
+          if (e0 > 0) issue_batch(e0);
 #pragma unroll
           for (int u = 0; u < kExtBatchFwd; ++u) {
             const int e = e0 + u;
@@ -221,6 +227,18 @@ mixed_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, floa
     Px<NPX> X, G, DX;
     mix_load<VEC>(X, x + img, HW, i, C);
     mix_load<VEC>(G, dy + img, HW, i, C);
+    float4 E[kExtBatch][3];
+    auto issue_batch = [&](int e0) {            // first batch before the classical candidates: its latency hides behind them
+#pragma unroll
+      for (int u = 0; u < kExtBatch; ++u) {
+        const int e = (e0 + u < RISP_MAX_BRANCHES) ? e0 + u : 0;
+        const bool live = (e0 + u < RISP_MAX_BRANCHES) && (e < d.K_ext) && !(wext[e] < 1e-9f);
+        const float* p = d.ext[e] + img + 4 * i;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) E[u][c] = ld_stream4_if(p + c * HW, live && c < C);
+      }
+    };
+    if (VEC == 4 && d.K_ext > 0) issue_batch(0);
 #pragma unroll
     for (int k = 0; k < NPX; ++k) { DX.b[k] = 0.f; DX.g[k] = 0.f; DX.r[k] = 0.f; }
 #pragma unroll
@@ -244,15 +262,7 @@ mixed_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, floa
 #pragma unroll
       for (int e0 = 0; e0 < RISP_MAX_BRANCHES; e0 += kExtBatch) {
         if (e0 < d.K_ext) {                                   // uniform
-          float4 E[kExtBatch][3];
-#pragma unroll
-          for (int u = 0; u < kExtBatch; ++u) {
-            const int e = (e0 + u < RISP_MAX_BRANCHES) ? e0 + u : 0;
-            const bool live = (e0 + u < RISP_MAX_BRANCHES) && (e < d.K_ext) && !(wext[e] < 1e-9f);
-            const float* p = d.ext[e] + img + 4 * i;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) E[u][c] = ld_stream4_if(p + c * HW, live && c < C);
-          }
+          if (e0 > 0) issue_batch(e0);
 #pragma unroll
           for (int u = 0; u < kExtBatch; ++u) {
             if (e0 + u < RISP_MAX_BRANCHES) {
