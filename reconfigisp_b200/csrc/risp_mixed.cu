@@ -59,6 +59,20 @@ template <> struct V3<1> {
 
 template <int VEC> struct MixNpx { static constexpr int value = (VEC == 4) ? 4 : 2; };
 
+// Compile-time list of the classical candidates (like the chain kernels' Sig<>): with SIG != 0 the op of candidate j is a
+// constant, so the interpreter's switch folds away and only that op's code and accumulators remain.  SIG == 0: generic.
+// The supernet's sRGB step (super_prune_fifteen_demos_four_bayer_two.py:101-171): gamma, grayworld-apply, skip, wbmanual,
+// wbquadratic, gtmmanual.
+#define RISP_MIX_SIG_SRGB ::risp::make_sig(RISP_OP_GAMMA, RISP_OP_GAIN_CLIP, RISP_OP_SKIP, RISP_OP_GAIN, RISP_OP_POLY10, RISP_OP_GTM)
+template <unsigned SIG>
+struct MixSig {
+  using SG = Sig<SIG>;
+  static constexpr bool generic = (SIG == 0);
+  __device__ __forceinline__ static bool live(const MixDesc& d, int j) { return generic ? (j < d.K_cls) : (j < SG::S); }
+  __device__ __forceinline__ static int op(const MixDesc& d, int j) { return generic ? d.op[j] : SG::op_c(j); }
+  __device__ __forceinline__ static int iarg(const MixDesc& d, int j) { return generic ? d.iarg[j] : 4; }
+};
+
 // 128-bit streaming load under a predicate (zeros when off): no branch, so the loads of a whole batch of candidate
 // outputs are in flight together instead of one dependent round trip per candidate
 __device__ __forceinline__ float4 ld_stream4_if(const float* p, bool on) {
@@ -118,7 +132,7 @@ __device__ __forceinline__ void mix_store(const Px<MixNpx<VEC>::value>& px, floa
 #ifndef RISP_MIX_FWD_MINB
 #define RISP_MIX_FWD_MINB 1
 #endif
-template <int VEC>
+template <int VEC, unsigned SIG>
 __global__ void __launch_bounds__(kT, RISP_MIX_FWD_MINB)
 mixed_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long HW, int C, MixDesc d,
                  const float* __restrict__ params, int pstride, const float* __restrict__ w) {
@@ -153,9 +167,9 @@ mixed_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long H
     for (int k = 0; k < NPX; ++k) { Y.b[k] = 0.f; Y.g[k] = 0.f; Y.r[k] = 0.f; }
 #pragma unroll
     for (int j = 0; j < RISP_MAX_STAGES; ++j) {
-      if (j < d.K_cls && !(wk[j] < 1e-9f)) {
+      if (MixSig<SIG>::live(d, j) && !(wk[j] < 1e-9f)) {
         Px<NPX> t = X;
-        stage_fwd(d.op[j], d.iarg[j], prow + d.off[j], t);
+        stage_fwd(MixSig<SIG>::op(d, j), MixSig<SIG>::iarg(d, j), prow + d.off[j], t);
 #pragma unroll
         for (int k = 0; k < NPX; ++k) {
           Y.b[k] = fmaf(wk[j], t.b[k], Y.b[k]); Y.g[k] = fmaf(wk[j], t.g[k], Y.g[k]); Y.r[k] = fmaf(wk[j], t.r[k], Y.r[k]);
@@ -197,7 +211,7 @@ mixed_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long H
   }
 }
 
-template <int VEC, bool BIG>
+template <int VEC, bool BIG, unsigned SIG>
 __global__ void __launch_bounds__(kT, 1)
 mixed_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx,
                  float* __restrict__ partial, long long HW, int C, MixDesc d, const float* __restrict__ params,
@@ -243,15 +257,15 @@ mixed_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, floa
     for (int k = 0; k < NPX; ++k) { DX.b[k] = 0.f; DX.g[k] = 0.f; DX.r[k] = 0.f; }
 #pragma unroll
     for (int j = 0; j < RISP_MAX_STAGES; ++j) {
-      if (j < d.K_cls && !(wk[j] < 1e-9f)) {
+      if (MixSig<SIG>::live(d, j) && !(wk[j] < 1e-9f)) {
         Px<NPX> t = X;
-        stage_fwd(d.op[j], d.iarg[j], prow + d.off[j], t);
+        stage_fwd(MixSig<SIG>::op(d, j), MixSig<SIG>::iarg(d, j), prow + d.off[j], t);
         float a = 0.f;
 #pragma unroll
         for (int k = 0; k < NPX; ++k) a = fmaf(G.b[k], t.b[k], fmaf(G.g[k], t.g[k], fmaf(G.r[k], t.r[k], a)));
         dot[j] += a;
         Px<NPX> dd = G;
-        stage_bwd<NPX, BIG>(d.op[j], d.iarg[j], prow + d.off[j], X, t, dd, accS[j], accB);
+        stage_bwd<NPX, BIG>(MixSig<SIG>::op(d, j), MixSig<SIG>::iarg(d, j), prow + d.off[j], X, t, dd, accS[j], accB);
 #pragma unroll
         for (int k = 0; k < NPX; ++k) {
           DX.b[k] = fmaf(wk[j], dd.b[k], DX.b[k]); DX.g[k] = fmaf(wk[j], dd.g[k], DX.g[k]); DX.r[k] = fmaf(wk[j], dd.r[k], DX.r[k]);
@@ -309,10 +323,10 @@ mixed_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, floa
   float bigw = 0.f;
 #pragma unroll
   for (int j = 0; j < RISP_MAX_STAGES; ++j) {
-    if (j < d.K_cls) {
+    if (MixSig<SIG>::live(d, j)) {
 #pragma unroll
       for (int q = 0; q < RISP_SMALL_ACC; ++q) accS[j][q] *= wk[j];
-      if (op_is_big(d.op[j])) bigw = wk[j];
+      if (op_is_big(MixSig<SIG>::op(d, j))) bigw = wk[j];
     }
   }
   __shared__ float red[kT / 32][kMixSlots];
@@ -352,6 +366,17 @@ mixed_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, floa
     for (int ww = 0; ww < kT / 32; ++ww) v += red[ww][slot];
     out[slot] = v;
   }
+}
+
+// signature of the classical candidate list (0: generic kernel)
+static unsigned mix_signature(const MixDesc& d, int C) {
+  if (C != 3 || d.K_cls < 1 || d.K_cls > 6) return 0;
+  unsigned sig = 0;
+  for (int j = 0; j < d.K_cls; ++j) {
+    if (d.op[j] == RISP_OP_GTM && d.iarg[j] != 4) return 0;
+    sig |= (unsigned)(d.op[j] + 1) << (4 * j);
+  }
+  return sig;
 }
 
 static int mix_blocks(int N, long long HW) {
@@ -520,8 +545,9 @@ static int mixed_fwd_impl(const float* x, float* y, int N, long long HW, int C, 
   for (int e = 0; e < K_ext; ++e) vec = vec && aligned16(ext[e]);
   dim3 grid(mix_blocks(N, HW), N);
   cudaStream_t st = as_stream(stream);
-  if (vec) mixed_fwd_kernel<4><<<grid, kT, 0, st>>>(x, y, HW, C, d, params, param_stride, w);
-  else mixed_fwd_kernel<1><<<grid, kT, 0, st>>>(x, y, HW, C, d, params, param_stride, w);
+  if (vec && mix_signature(d, C) == RISP_MIX_SIG_SRGB) mixed_fwd_kernel<4, RISP_MIX_SIG_SRGB><<<grid, kT, 0, st>>>(x, y, HW, C, d, params, param_stride, w);
+  else if (vec) mixed_fwd_kernel<4, 0><<<grid, kT, 0, st>>>(x, y, HW, C, d, params, param_stride, w);
+  else mixed_fwd_kernel<1, 0><<<grid, kT, 0, st>>>(x, y, HW, C, d, params, param_stride, w);
   return check_launch("mixed_fwd_kernel");
 }
 
@@ -556,9 +582,10 @@ static int mixed_bwd_impl(const float* x, const float* dy, float* dx, float* dw,
   dim3 grid(B, N);
   cudaStream_t st = as_stream(stream);
   float* partial = static_cast<float*>(workspace);
-#define RISP_MIXB(V, BG) mixed_bwd_kernel<V, BG><<<grid, kT, 0, st>>>(x, dy, dx, partial, HW, C, d, params, param_stride, w)
-  if (vec) { if (big) RISP_MIXB(4, true); else RISP_MIXB(4, false); }
-  else     { if (big) RISP_MIXB(1, true); else RISP_MIXB(1, false); }
+#define RISP_MIXB(V, BG, SG) mixed_bwd_kernel<V, BG, SG><<<grid, kT, 0, st>>>(x, dy, dx, partial, HW, C, d, params, param_stride, w)
+  if (vec && mix_signature(d, C) == RISP_MIX_SIG_SRGB) RISP_MIXB(4, true, RISP_MIX_SIG_SRGB);
+  else if (vec) { if (big) RISP_MIXB(4, true, 0); else RISP_MIXB(4, false, 0); }
+  else          { if (big) RISP_MIXB(1, true, 0); else RISP_MIXB(1, false, 0); }
 #undef RISP_MIXB
   rc = check_launch("mixed_bwd_kernel");
   if (rc != RISP_OK) return rc;
