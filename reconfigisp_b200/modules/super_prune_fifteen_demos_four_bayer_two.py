@@ -163,6 +163,15 @@ class SuperPruneFifteenDemosFourBayerTwo(nn.Module):
             o.record_stream(main)
         return outs
 
+    def _table_affine(self, device):
+        """[0,1] -> kernel range of the classical candidates' parameters as one affine map over the 37 table entries."""
+        t = self.__dict__.get('_affine')
+        if t is None or t[0].device != device:
+            scale = torch.tensor([1.0] + [5.0] * 3 + [10.0] * 30 + [1.0] * 3, device=device).view(1, -1)
+            shift = torch.tensor([0.0] + [0.0] * 3 + [-5.0] * 30 + [0.0] * 3, device=device).view(1, -1)
+            t = self._affine = (scale, shift)
+        return t
+
     def forward(self, x):
         """x: (N,1,H,W) RGGB -> (N,3,H,W) BGR."""
         N = x.size(0)
@@ -202,18 +211,27 @@ class SuperPruneFifteenDemosFourBayerTwo(nn.Module):
         for s in range(self.n_step):
             post, host = posts[2 + s]
             mods, pars = self.all_modules[2 + s], self.all_params[2 + s]
-            sig = lambda i: torch.sigmoid(pars[i]).view(1, -1)
-            # kernel-level parameter table of the classical candidates, one row per image
+            # sigmoid of ALL parameter logits of the step in one launch (one cat, one sigmoid; the per-candidate values are views)
+            sizes = [p.nelement() for p in pars]
+            sg_all = torch.sigmoid(torch.cat([p.view(-1) for p in pars if p.nelement()]))
+            offs, o = [], 0
+            for n_ in sizes:
+                offs.append(o)
+                o += n_
+            sig = lambda i: sg_all[offs[i]:offs[i] + sizes[i]].view(1, -1)
+            # kernel-level parameter table of the classical candidates, one row per image:
+            # [gamma | grayworld gains | wbmanual p*5 | wbquadratic p*10-5 | gtm knots]  (tools_origin.py:214, :326)
             gw = grayworld_gains(x) if not host[4] < 1e-9 else torch.ones((N, 3), device=x.device)
-            table = torch.cat([sig(0).expand(N, 1), gw, (sig(10) * 5).expand(N, 3), (sig(12) * 10 - 5).expand(N, 30),
-                               sig(13).expand(N, 3)], dim=1)
+            scale, shift = self._table_affine(x.device)
+            row = torch.addcmul(shift, torch.cat([sig(0), sig(10), sig(12), sig(13)], dim=1), scale)       # (1, 37)
+            table = torch.cat([row[:, :1].expand(N, 1), gw, row[:, 1:].expand(N, 36)], dim=1)
             jobs, widx = [], list(cls_idx)
             pruned = [i for i in range(15) if host[i] < 1e-9]
             for i in range(15):
                 if i in cls_idx or host[i] < 1e-9:
                     continue
                 par = pars[i]
-                par_tensor = None if par.nelement() == 0 else torch.sigmoid(par).repeat(N, 1)
+                par_tensor = None if par.nelement() == 0 else sig(i).expand(N, -1)
                 jobs.append(lambda i=i, x=x, p=par_tensor: mods[i](x, p))
                 widx.append(i)
             if jobs:
