@@ -65,7 +65,10 @@ __device__ __forceinline__ void row_finish(float (&dst)[4 + 2 * HL], const Row<H
 }
 
 // F: struct with  __device__ void operator()(const float (&w)[NP][2*HL+1][4+2*HL], float (&out)[NP][4], int zp) const
-template <int HL, int NP, int BORDER, class F>
+#ifndef RISP_MARCH_DEPTH
+#define RISP_MARCH_DEPTH 3
+#endif
+template <int HL, int NP, int BORDER, class F, int D = RISP_MARCH_DEPTH>
 __global__ void __launch_bounds__(kWarps * 32)
 march_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int rows_per_chunk, F f) {
   constexpr int WR = 2 * HL + 1, WC = 4 + 2 * HL;
@@ -80,34 +83,33 @@ march_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, i
   float* __restrict__ yb = y + (long long)zp * NP * plane;
   const int ra = blockIdx.y * rows_per_chunk, rb = min(H, ra + rows_per_chunk);
   float w[NP][WR][WC];
-  Row<HL> q[NP], q2[NP];       // two rows in flight: at 32 warps per SM one 512-byte row per warp does not cover the HBM latency
+  Row<HL> qq[D][NP];           // D rows in flight per warp: at ~32 warps per SM one 512-byte row per warp does not cover the HBM latency
 #pragma unroll
   for (int j = 0; j < WR - 1; ++j) {
     const long long ro = (long long)brow<BORDER>(ra - HL + j, H) * W;
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
-      row_issue<HL>(q[p], xb + p * plane + ro, W, c0, active, lane);
-      row_finish<HL, BORDER>(w[p][j], q[p], W, c0, active, lane);
+      row_issue<HL>(qq[0][p], xb + p * plane + ro, W, c0, active, lane);
+      row_finish<HL, BORDER>(w[p][j], qq[0][p], W, c0, active, lane);
     }
   }
-  {
-    const long long ro = (long long)brow<BORDER>(ra + HL, H) * W, ro2 = (long long)brow<BORDER>(ra + 1 + HL, H) * W;
 #pragma unroll
-    for (int p = 0; p < NP; ++p) {
-      row_issue<HL>(q[p], xb + p * plane + ro, W, c0, active, lane);
-      row_issue<HL>(q2[p], xb + p * plane + ro2, W, c0, active, lane);
-    }
+  for (int d = 0; d < D; ++d) {
+    const long long ro = (long long)brow<BORDER>(ra + d + HL, H) * W;      // rows past the chunk are loaded and dropped
+#pragma unroll
+    for (int p = 0; p < NP; ++p) row_issue<HL>(qq[d][p], xb + p * plane + ro, W, c0, active, lane);
   }
   for (int r = ra; r < rb; ++r) {
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
-      row_finish<HL, BORDER>(w[p][WR - 1], q[p], W, c0, active, lane);
-      q[p] = q2[p];
-    }
-    if (r + 2 < rb) {
-      const long long ro = (long long)brow<BORDER>(r + 2 + HL, H) * W;
+      row_finish<HL, BORDER>(w[p][WR - 1], qq[0][p], W, c0, active, lane);
 #pragma unroll
-      for (int p = 0; p < NP; ++p) row_issue<HL>(q2[p], xb + p * plane + ro, W, c0, active, lane);
+      for (int d = 0; d + 1 < D; ++d) qq[d][p] = qq[d + 1][p];
+    }
+    if (r + D < rb) {
+      const long long ro = (long long)brow<BORDER>(r + D + HL, H) * W;
+#pragma unroll
+      for (int p = 0; p < NP; ++p) row_issue<HL>(qq[D - 1][p], xb + p * plane + ro, W, c0, active, lane);
     }
     float out[NP][4];
     f(w, out, zp);

@@ -399,16 +399,24 @@ sharpen_bwd_dx_kernel(const float* __restrict__ e, float* __restrict__ dx, int H
 
 // ---- register-marching fast paths (risp_march.cuh) -----------------------------------------------------------
 struct Median3F {
+  // exact median of 9 with the columns shared by the 4 pixels of a lane: sort every window column (3 compare-exchanges),
+  // then  median9 = med3( max of the column minima, med3 of the column medians, min of the column maxima )  -- 21 min/max per
+  // pixel instead of the 38 of a 19-exchange network per pixel
+  __device__ __forceinline__ static float med3(float a, float b, float c) { return fmaxf(fminf(a, b), fminf(fmaxf(a, b), c)); }
   __device__ __forceinline__ void operator()(const float (&w)[1][3][6], float (&o)[1][4], int) const {
+    float lo[6], mid[6], hi[6];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float v[9];
-#pragma unroll
-      for (int j = 0; j < 3; ++j)
-#pragma unroll
-        for (int i = 0; i < 3; ++i) v[j * 3 + i] = w[0][j][k + i];
-      o[0][k] = median9(v);
+    for (int i = 0; i < 6; ++i) {
+      const float a = w[0][0][i], b = w[0][1][i], c = w[0][2][i];
+      const float mn = fminf(a, b), mx = fmaxf(a, b);
+      lo[i] = fminf(mn, c);
+      hi[i] = fmaxf(mx, c);
+      mid[i] = fmaxf(mn, fminf(mx, c));
     }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      o[0][k] = med3(fmaxf(fmaxf(lo[k], lo[k + 1]), lo[k + 2]), med3(mid[k], mid[k + 1], mid[k + 2]),
+                     fminf(fminf(hi[k], hi[k + 1]), hi[k + 2]));
   }
 };
 struct SharpenF {
@@ -542,7 +550,7 @@ extern "C" int risp_sharpen_fwd(const float* x, float* y, int N, int H, int W, c
   RISP_REQUIRE((long long)N * 3 <= 65535, RISP_E_INVALID, "risp_sharpen_fwd: batch too large");
   if (march::usable(x, y, H, W, 2)) {
     const march::Geom g = march::geometry(H, W, N * 3);
-    march::march_kernel<2, 1, march::REFLECT101, SharpenF><<<g.grid, march::kWarps * 32, 0, as_stream(stream)>>>(
+    march::march_kernel<2, 1, march::REFLECT101, SharpenF, 2><<<g.grid, march::kWarps * 32, 0, as_stream(stream)>>>(
         x, y, H, W, g.rows_per_chunk, SharpenF{amount});
     return check_launch("march_kernel<sharpen>");
   }
