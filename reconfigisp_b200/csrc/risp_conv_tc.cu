@@ -791,6 +791,7 @@ static int conv_tc_dispatch(const ConvTcArgs& a, int N, int K, int NP, cudaStrea
       // CTA with one resident CTA 1500 us
       if (NP == 64 && g_tc_variant == 1) RISP_TC(3, 4, 64, 2, 1, 2, 2, 3);
       if (NP == 64 && g_tc_variant == 2) RISP_TC(3, 2, 64, 2, 2, 1, 2, 3);
+      if (NP == 64 && g_tc_variant == 3) RISP_TC(3, 2, 64, 3, 2, 2, 2, 1);
       switch (NP) { case 16: RISP_TC(3, 8, 16, 2, 2, 1, 1, 3); case 32: RISP_TC(3, 4, 32, 2, 2, 1, 2, 3); case 48: RISP_TC(3, 2, 48, 2, 2, 1, 2, 3); default: RISP_TC(3, 2, 64, 3, 2, 2, 1, 1); }
     case 5:
       switch (NP) { case 16: RISP_TC(5, 4, 16, 4, 2, 1, 1, 1); case 32: RISP_TC(5, 4, 32, 4, 2, 1, 1, 1); case 48: RISP_TC(5, 2, 48, 2, 2, 1, 1, 1); default: RISP_TC(5, 2, 64, 2, 2, 1, 1, 1); }

@@ -7,7 +7,7 @@ for B in (4, 64):
     x = torch.randn(B, 64, 256, 256, device='cuda'); w = torch.randn(64, 64, 3, 3, device='cuda') / 24.0; b = torch.zeros(64, device='cuda')
     xb = ops.to_blocked(x)
     ref = None
-    for v in (0, 1, 2):
+    for v in (0, 1, 2, 3):
         L.call('risp_debug_tc_variant', v)
         with torch.no_grad():
             for _ in range(3):
