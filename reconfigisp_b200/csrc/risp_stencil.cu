@@ -291,6 +291,115 @@ guided_out_kernel(const float* __restrict__ x, const float* __restrict__ a_in, c
   y[o] = sa * inv * x[o] + sb * inv;
 }
 
+// ---- guided filter, marching version (W % 4 == 0): running column sums in registers, horizontal window by shuffles ----
+// A warp owns a strip of 128 loaded columns (112 output columns + an 8-column halo on both sides = kMaxR) and walks down a
+// chunk of rows.  Every lane keeps the VERTICAL running sums of its 4 columns over the 2R+1 rows of the window (one row
+// enters, one row leaves per step: two coalesced 128-bit loads per lane, the leaving row comes from L2), and the HORIZONTAL
+// window sum of those column sums is gathered from the neighbouring lanes by shuffles -- no shared memory, no barrier, and
+// (2R+1) + 2 adds per pixel and quantity instead of the tile kernels' 2(2R+1) shared-memory reads.  Two passes as before:
+// (a, b) from x, then y = mean(a) x + mean(b).
+namespace gmarch {
+constexpr int kHalo = kMaxR, kOutCols = 128 - 2 * kHalo, kWarps = 4;
+
+__device__ __forceinline__ int refl(int i, int n) {
+  while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+  return i;
+}
+// 4 consecutive columns [c, c+4) of row q (both reflect-101); c is a multiple of 4
+__device__ __forceinline__ float4 load4(const float* __restrict__ plane, int H, int W, int q, int c) {
+  const float* row = plane + (long long)refl(q, H) * W;
+  if (c >= 0 && c + 4 <= W) return __ldg(reinterpret_cast<const float4*>(row + c));
+  return make_float4(row[refl(c, W)], row[refl(c + 1, W)], row[refl(c + 2, W)], row[refl(c + 3, W)]);
+}
+// window sums over columns k-R .. k+R (k = the lane's 4 columns) of a quantity whose per-column values are v (this lane)
+template <int R>
+__device__ __forceinline__ void hbox(const float (&v)[4], float (&out)[4]) {
+  constexpr int NL = (R + 3) / 4;                    // neighbour lanes needed on each side
+  float e[4 * (2 * NL + 1)];
+#pragma unroll
+  for (int dl = -NL; dl <= NL; ++dl)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      // lanes at the ends of the warp receive their own value for out-of-range sources; those lanes are halo-only
+      e[(dl + NL) * 4 + i] = (dl == 0) ? v[i] : (dl < 0 ? __shfl_up_sync(0xffffffffu, v[i], -dl) : __shfl_down_sync(0xffffffffu, v[i], dl));
+    }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float s = 0.f;
+#pragma unroll
+    for (int d = -R; d <= R; ++d) s += e[NL * 4 + k + d];
+    out[k] = s;
+  }
+}
+
+template <int R, int PASS>      // PASS 0: x -> (a, b);  PASS 1: (a, b, x) -> y
+__global__ void __launch_bounds__(kWarps * 32)
+guided_march_kernel(const float* __restrict__ x, float* __restrict__ a_buf, float* __restrict__ b_buf, float* __restrict__ y,
+                    int H, int W, int rows_per_chunk, float eps) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int strip = blockIdx.x * kWarps + wid;
+  if (strip * kOutCols >= W) return;
+  const int c = strip * kOutCols - kHalo + lane * 4;              // first of this lane's 4 columns (may lie outside the frame)
+  const long long plane = (long long)H * W;
+  const float* __restrict__ p0 = (PASS == 0 ? x : a_buf) + (long long)blockIdx.z * plane;
+  const float* __restrict__ p1 = (PASS == 0 ? x : b_buf) + (long long)blockIdx.z * plane;
+  const int ra = blockIdx.y * rows_per_chunk, rb = min(H, ra + rows_per_chunk);
+  if (ra >= rb) return;
+  const bool writer = lane >= kHalo / 4 && lane < 32 - kHalo / 4 && c < W;
+  float v0[4] = {0.f, 0.f, 0.f, 0.f}, v1[4] = {0.f, 0.f, 0.f, 0.f};   // running column sums: PASS 0: x, x^2 ; PASS 1: a, b
+  auto add_row = [&](int q, float sgn) {
+    const float4 t = load4(p0, H, W, q, c);
+    const float tv[4] = {t.x, t.y, t.z, t.w};
+    if (PASS == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { v0[i] = fmaf(sgn, tv[i], v0[i]); v1[i] = fmaf(sgn * tv[i], tv[i], v1[i]); }
+    } else {
+      const float4 u = load4(p1, H, W, q, c);
+      const float uv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { v0[i] = fmaf(sgn, tv[i], v0[i]); v1[i] = fmaf(sgn, uv[i], v1[i]); }
+    }
+  };
+  for (int d = -R; d <= R; ++d) add_row(ra + d, 1.f);
+  const float inv = 1.f / (float)((2 * R + 1) * (2 * R + 1));
+  for (int r = ra; r < rb; ++r) {
+    float s0[4], s1[4];
+    hbox<R>(v0, s0);
+    hbox<R>(v1, s1);
+    if (writer) {
+      const long long o = (long long)blockIdx.z * plane + (long long)r * W + c;
+      if (PASS == 0) {
+        float av[4], bv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float mean = s0[i] * inv, var = s1[i] * inv - mean * mean;
+          av[i] = var / (var + eps);
+          bv[i] = mean - av[i] * mean;
+        }
+        *reinterpret_cast<float4*>(a_buf + o) = make_float4(av[0], av[1], av[2], av[3]);
+        *reinterpret_cast<float4*>(b_buf + o) = make_float4(bv[0], bv[1], bv[2], bv[3]);
+      } else {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + o));
+        st_stream4(y + o, make_float4(fmaf(s0[0] * inv, xv.x, s1[0] * inv), fmaf(s0[1] * inv, xv.y, s1[1] * inv),
+                                      fmaf(s0[2] * inv, xv.z, s1[2] * inv), fmaf(s0[3] * inv, xv.w, s1[3] * inv)));
+      }
+    }
+    if (r + 1 < rb) { add_row(r + 1 + R, 1.f); add_row(r - R, -1.f); }
+  }
+}
+
+template <int R>
+static void launch(const float* x, float* a, float* b, float* y, int N, int H, int W, float eps, cudaStream_t st) {
+  const int strips = (int)cdiv(W, kOutCols), bx = (int)cdiv(strips, kWarps);
+  long long chunks = cdiv((long long)sm_count() * 8, (long long)bx * N * 3);
+  int rows = (int)cdiv(H, chunks < 1 ? 1 : chunks);
+  rows = rows < 48 ? 48 : rows;                                      // a chunk start costs 2R+1 rows of loads
+  dim3 grid((unsigned)bx, (unsigned)cdiv(H, rows), (unsigned)(N * 3));
+  guided_march_kernel<R, 0><<<grid, kWarps * 32, 0, st>>>(x, a, b, y, H, W, rows, eps);
+  guided_march_kernel<R, 1><<<grid, kWarps * 32, 0, st>>>(x, a, b, y, H, W, rows, eps);
+}
+}  // namespace gmarch
+
 // ---- sharpen (unsharp mask, 5x5 binomial) ------------------------------------------------------------------
 __constant__ float kBinom[5] = {1.f / 16, 4.f / 16, 6.f / 16, 4.f / 16, 1.f / 16};
 
@@ -539,6 +648,19 @@ extern "C" int risp_guided_fwd(const float* x, float* y, int N, int H, int W, in
   cudaStream_t st = as_stream(stream);
   float* a = static_cast<float*>(workspace);
   float* b = a + (size_t)N * 3 * H * W;
+  if (W % 4 == 0 && aligned16(x) && aligned16(y) && aligned16(a) && aligned16(b) && H > radius && W > radius && cdiv(H, 48) <= 65535) {
+    switch (radius) {
+      case 1: gmarch::launch<1>(x, a, b, y, N, H, W, eps, st); break;
+      case 2: gmarch::launch<2>(x, a, b, y, N, H, W, eps, st); break;
+      case 3: gmarch::launch<3>(x, a, b, y, N, H, W, eps, st); break;
+      case 4: gmarch::launch<4>(x, a, b, y, N, H, W, eps, st); break;
+      case 5: gmarch::launch<5>(x, a, b, y, N, H, W, eps, st); break;
+      case 6: gmarch::launch<6>(x, a, b, y, N, H, W, eps, st); break;
+      case 7: gmarch::launch<7>(x, a, b, y, N, H, W, eps, st); break;
+      default: gmarch::launch<8>(x, a, b, y, N, H, W, eps, st); break;
+    }
+    return check_launch("guided_march_kernel");
+  }
   guided_ab_kernel<<<tile_grid(H, W, N * 3), kT, tile_smem(radius, 1) + 2 * sizeof(float) * (TH + 2 * radius) * TW, st>>>(x, a, b, H, W, radius, eps);
   guided_out_kernel<<<tile_grid(H, W, N * 3), kT, tile_smem(radius, 2) + 2 * sizeof(float) * (TH + 2 * radius) * TW, st>>>(x, a, b, y, H, W, radius);
   return check_launch("guided kernels");

@@ -540,3 +540,18 @@ def test_stencil_marching_fast_paths(ops, shape):
     a = torch.tensor([[0.7], [1.5], [0.2]][:N])
     if H > 2:
         assert maxabs(ops.sharpen(dev(x), dev(a)), O.sharpen(x, a)) <= TOL
+
+
+@pytest.mark.parametrize('shape', [(2, 37, 44), (1, 9, 8), (1, 130, 260), (2, 61, 45)])
+@pytest.mark.parametrize('radius', [1, 3, 4, 8])
+def test_guided_filter_marching_and_tile_kernels_match_oracle(ops, shape, radius):
+    """W % 4 == 0 takes the register-marching kernels (running column sums + shuffle windows, strips with an 8-column halo,
+    several strips / row chunks at the larger shape), other widths the shared-memory tile kernels; both against the oracle,
+    including a flat region where var -> 0 (the cancellation-sensitive case of s2/n - mean^2)."""
+    N, H, W = shape
+    if min(H, W) <= radius:
+        pytest.skip('window larger than the frame')
+    x = rand_img(N, H, W, 31 + radius, 0.0, 1.0)
+    x[:, :, : H // 3, : W // 2] = 0.37
+    for eps in (1e-2, 1e-3):
+        assert maxabs(ops.guided_filter(dev(x), radius, eps), O.guided_filter(x, radius, eps)) <= TOL, (shape, radius, eps)
