@@ -43,6 +43,12 @@ def _worker(rank, world, port, out):
     gathered = [torch.zeros(216) for _ in range(world)]
     dist.all_gather(gathered, p.detach())
     assert torch.equal(gathered[0], gathered[1])
+    # in-place average of a contiguous buffer (the tuning step's exchange when the peer-memory path is unavailable), and the
+    # peer-memory reducer declining -- on every rank alike -- anything but a single-node NCCL group
+    flat = torch.arange(8, dtype=torch.float32) * (rank + 1)
+    D.allreduce_mean_(flat)
+    assert torch.allclose(flat, torch.arange(8, dtype=torch.float32) * 1.5)
+    assert D.P2PAllReduce.create() is None
     sl = D.shard_batch(8, rank, world)
     assert (sl.start, sl.stop) == (4 * rank, 4 * rank + 4)
     out.put((rank, float(p.detach().sum())))
@@ -69,3 +75,11 @@ def test_single_process_is_a_no_op():
     t = [torch.ones(3), None]
     out = D.allreduce_mean_flat(t)
     assert out[0] is t[0] and out[1] is None and not D.is_dist()
+    assert D.P2PAllReduce.create() is None
+
+
+def test_p2p_buffer_layout_is_sized_by_the_library():
+    """Host-only entry: slots[2][world][cap] floats + flags[2][world] + epoch + timeout counter."""
+    from reconfigisp_b200 import _lib as L
+    assert L.size('risp_p2p_buffer_bytes', 8, 1024) == 4 * 2 * 8 * 1024 + 4 * (2 * 8 + 2)
+    assert L.size('risp_p2p_buffer_bytes', 9, 1024) == 0 and L.size('risp_p2p_buffer_bytes', 2, 0) == 0

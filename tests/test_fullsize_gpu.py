@@ -132,3 +132,62 @@ def test_full_frame_linear_and_index_properties(ops, frame):
     assert tiles.shape[0] == 63
     back = ops.patch2whole(tiles, (H, W), (480, 480))
     assert float((back - gt[0]).abs().max()) <= 1e-6, float((back - gt[0]).abs().max())
+
+
+def test_full_frame_stencils_match_oracle_on_crops(ops, frame):
+    """Register-marching stencils at 12 MP (many strips / row chunks / running sums over long chunks): median 3x3 bit-exact and
+    the guided filter within tolerance against the oracle on interior and border crops (the oracle sees the crop + halo; on
+    the frame border the crop includes the border itself, so the border rules are compared too)."""
+    raw, gt = frame
+    x = gt.cuda()                                           # (1,3,H,W) in [0,1]
+    x255 = x * 255
+    med = ops.median(x255, 3)
+    gf = ops.guided_filter(x, 4, 1e-3)
+    halo = 8
+    for (y0, x0) in ((0, 0), (0, W - 160), (H - 96, 0), (H - 96, W - 160), (1480, 2000), (777, 3880)):
+        h, w = 96, 160
+        ya, yb, xa, xb = max(0, y0 - halo), min(H, y0 + h + halo), max(0, x0 - halo), min(W, x0 + w + halo)
+        # crops that touch the frame border keep it (same border rule); inner edges carry a halo that is cut off again
+        cy, cx = y0 - ya, x0 - xa
+        crop = x[:, :, ya:yb, xa:xb].cpu()
+        m_ref = O.denoise_median(crop * 255, 3)[:, :, cy:cy + h, cx:cx + w]
+        assert torch.equal(med[:, :, y0:y0 + h, x0:x0 + w].cpu(), m_ref), (y0, x0)
+        g_ref = O.guided_filter(crop, 4, 1e-3)[:, :, cy:cy + h, cx:cx + w]
+        assert float((gf[:, :, y0:y0 + h, x0:x0 + w].cpu() - g_ref).abs().max()) <= 1e-4, (y0, x0)
+
+
+def test_mixed_op_specialised_kernel_matches_sum_of_candidates(ops):
+    """The supernet's sRGB mixed-op at 2 MP (compile-time candidate signature, batched candidate loads, many blocks) against
+    the same weighted sum built from the single-candidate chain kernels + torch, forward and every gradient."""
+    from reconfigisp_b200.modules.super_prune_fifteen_demos_four_bayer_two import SRGB_CLASSICAL
+    g = torch.Generator().manual_seed(21)
+    N, Hh, Ww, K_ext = 2, 1000, 1000, 9
+    dev = 'cuda'
+    x = torch.rand(N, 3, Hh, Ww, generator=g).to(dev).requires_grad_()
+    ext = [torch.rand(N, 3, Hh, Ww, generator=g).to(dev).requires_grad_() for _ in range(K_ext)]
+    ident = [0.0] * 30
+    ident[6] = ident[17] = ident[28] = 1.0
+    row = torch.tensor([0.6, 1.1, 0.9, 1.05, 1.05, 1.0, 0.95] + ident + [0.3, 0.5, 0.8]) + torch.randn(40, generator=g) * 0.01
+    table = row.view(1, -1).repeat(N, 1).to(dev).requires_grad_()
+    w = torch.softmax(torch.randn(len(SRGB_CLASSICAL) + K_ext, generator=g), 0).to(dev).requires_grad_()
+    dy = torch.randn(N, 3, Hh, Ww, generator=g).to(dev)
+    chain = ops.Chain([op for _, op in SRGB_CLASSICAL])
+    y = ops.mixed_op(x, chain, table, w, ext)
+    got = torch.autograd.grad(y, [x, table, w] + ext, dy)
+    # reference: one chain kernel per classical candidate on its slice of the table
+    offs, o = [], 0
+    for _, op in SRGB_CLASSICAL:
+        c1 = ops.Chain([op])
+        offs.append((o, c1.P, c1))
+        o += c1.P
+    yr = 0
+    for j, (o0, P, c1) in enumerate(offs):
+        t = x if P == 0 and c1.names == ['skip'] else ops.chain_apply(x, c1, table[:, o0:o0 + P] if P else None)
+        yr = yr + w[j] * t
+    for e in range(K_ext):
+        yr = yr + w[len(offs) + e] * ext[e]
+    ref = torch.autograd.grad(yr, [x, table, w] + ext, dy)
+    assert float((y - yr).detach().abs().max()) <= 2e-6
+    for a, b in zip(got, ref):
+        scale = max(1e-6, float(b.abs().max()))
+        assert float((a - b).abs().max()) <= 2e-4 * scale, (a.shape, float((a - b).abs().max()), scale)
