@@ -337,6 +337,9 @@ int risp_conv_tc_fwd(const float* x_blk, const float* mask_in_blk, const float* 
 int risp_conv_tc_fwd_tab(const float* x_blk, const float* mask_in_blk, const float* wprep, const float* bias,
                          const float* bias_tab, const float* res_blk, const float* mask_out_blk, float* y_blk,
                          float* y_planar, int N, int Cin, int Cout, int H, int W, int K, int flags, risp_stream_t stream);
+/* the table itself: tab (N, J) = b (J) + feat (N, F) x S (F, J) with J = K*K*pad16(Cout), F <= 32; and d feat = d tab x S^T */
+int risp_bias_table_fwd(const float* feat, const float* S, const float* b, float* tab, int N, int F, int J, risp_stream_t stream);
+int risp_bias_table_bwd(const float* dtab, const float* S, float* dfeat, int N, int F, int J, risp_stream_t stream);
 size_t risp_blocked_class_sums_workspace(int N, int C, int H, int K);
 int risp_blocked_class_sums(const float* g_blk, const float* mask_blk, float* out, int N, int C, int CP, int H, int W, int K,
                             void* workspace, size_t workspace_bytes, risp_stream_t stream);

@@ -732,6 +732,54 @@ extern "C" int risp_from_blocked(const float* blocked, float* planar, int N, int
   return check_launch("from_blocked_kernel");
 }
 
+// ---- the bias table itself: tab (N, J) = b (J) + feat (N, F) x S (F, J), and d feat = d tab x S^T -----------------------
+// F = 9 + P <= 32 features, J = K*K*CoutPad (5184 for SRCNNRes); S is constant.  Two trivial kernels instead of cuBLAS's
+// gemv (which needs ~85 us for this shape) / an elementwise product + row sums.
+namespace risp {
+__global__ void __launch_bounds__(256)
+bias_table_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ S, const float* __restrict__ b, float* __restrict__ tab,
+                      int F, int J) {
+  const int n = blockIdx.y;
+  __shared__ float f_s[32];
+  if (threadIdx.x < F) f_s[threadIdx.x] = feat[n * F + threadIdx.x];
+  __syncthreads();
+  for (int j = blockIdx.x * 256 + threadIdx.x; j < J; j += gridDim.x * 256) {
+    float acc = b[j];
+    for (int f = 0; f < F; ++f) acc = fmaf(f_s[f], __ldg(S + (long long)f * J + j), acc);
+    tab[(long long)n * J + j] = acc;
+  }
+}
+__global__ void __launch_bounds__(256)
+bias_table_bwd_kernel(const float* __restrict__ dtab, const float* __restrict__ S, float* __restrict__ dfeat, int F, int J) {
+  const int f = blockIdx.x, n = blockIdx.y;                  // one CTA per output element, fixed summation order
+  float acc = 0.f;
+  for (int j = threadIdx.x; j < J; j += 256) acc = fmaf(dtab[(long long)n * J + j], __ldg(S + (long long)f * J + j), acc);
+  __shared__ float red[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    dfeat[n * F + f] = t;
+  }
+}
+}  // namespace risp
+
+extern "C" int risp_bias_table_fwd(const float* feat, const float* S, const float* b, float* tab, int N, int F, int J,
+                                   risp_stream_t stream) {
+  RISP_REQUIRE(feat && S && b && tab && N > 0 && N <= 65535 && F >= 1 && F <= 32 && J >= 1, RISP_E_INVALID, "risp_bias_table_fwd: bad arguments");
+  const int bx = (int)(cdiv(J, 256) > 64 ? 64 : cdiv(J, 256));
+  risp::bias_table_fwd_kernel<<<dim3((unsigned)bx, (unsigned)N), 256, 0, as_stream(stream)>>>(feat, S, b, tab, F, J);
+  return check_launch("bias_table_fwd_kernel");
+}
+
+extern "C" int risp_bias_table_bwd(const float* dtab, const float* S, float* dfeat, int N, int F, int J, risp_stream_t stream) {
+  RISP_REQUIRE(dtab && S && dfeat && N > 0 && N <= 65535 && F >= 1 && F <= 32 && J >= 1, RISP_E_INVALID, "risp_bias_table_bwd: bad arguments");
+  risp::bias_table_bwd_kernel<<<dim3((unsigned)F, (unsigned)N), 256, 0, as_stream(stream)>>>(dtab, S, dfeat, F, J);
+  return check_launch("bias_table_bwd_kernel");
+}
+
 extern "C" size_t risp_blocked_class_sums_workspace(int N, int C, int H, int K) {
   return (N > 0 && C > 0 && H > 0 && K > 0) ? sizeof(float) * (size_t)N * H * K * ((C + 3) / 4 * 4) : 0;
 }
