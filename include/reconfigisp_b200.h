@@ -340,6 +340,20 @@ int risp_conv_tc_fwd_tab(const float* x_blk, const float* mask_in_blk, const flo
 /* the table itself: tab (N, J) = b (J) + feat (N, F) x S (F, J) with J = K*K*pad16(Cout), F <= 32; and d feat = d tab x S^T */
 int risp_bias_table_fwd(const float* feat, const float* S, const float* b, float* tab, int N, int F, int J, risp_stream_t stream);
 int risp_bias_table_bwd(const float* dtab, const float* S, float* dfeat, int N, int F, int J, risp_stream_t stream);
+/* Grouped launches for a BANK of networks with identical layer shapes (the eight SRCNNRes proxies of a supernet step,
+ * super_prune_fifteen_demos_four_bayer_two.py:101-171): G <= 8 groups x N_per_group images in ONE launch.  The output,
+ * masks and bias table have G*N_per_group images; group g uses the prepared weights at wprep + slots[g]*w_group_floats,
+ * the bias at bias + slots[g]*bias_group_floats, S / b of the table at slot slots[g]; with x_shared / res_shared the
+ * input / residual have N_per_group images that every group reads.  slots: HOST array of G ints. */
+int risp_conv_tc_fwd_grouped(const float* x_blk, const float* mask_in_blk, const float* wprep, const float* bias,
+                             const float* bias_tab, const float* res_blk, const float* mask_out_blk, float* y_blk,
+                             float* y_planar, int G, int N_per_group, const int* slots, long long w_group_floats,
+                             int bias_group_floats, int x_shared, int res_shared, int Cin, int Cout, int H, int W,
+                             int K, int flags, risp_stream_t stream);
+int risp_bias_table_fwd_grouped(const float* feat, const float* S, const float* b, float* tab, int G, int N_per_group,
+                                const int* slots, int F, int J, risp_stream_t stream);
+int risp_bias_table_bwd_grouped(const float* dtab, const float* S, float* dfeat, int G, int N_per_group, const int* slots,
+                                int F, int J, risp_stream_t stream);
 size_t risp_blocked_class_sums_workspace(int N, int C, int H, int K);
 int risp_blocked_class_sums(const float* g_blk, const float* mask_blk, float* out, int N, int C, int CP, int H, int W, int K,
                             void* workspace, size_t workspace_bytes, risp_stream_t stream);

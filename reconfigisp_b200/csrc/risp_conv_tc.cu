@@ -40,6 +40,13 @@ struct ConvTcArgs {
   int CinG, Cout, CoutPad, H, W, flags;
   int Cin;               // real input channels: only ceil(Cin/8) chunks are multiplied (the rest of the layout is zero padding)
   int w_chunks;          // chunks the weights were prepared with (the lo block follows the hi block of ALL chunks)
+  // grouped launch (a bank of networks with identical layer shapes, e.g. the eight SRCNNRes proxies of a supernet step):
+  // blockIdx.y = g * n_per_group + n; group g uses weight / bias slot gslot[g]; x and res may be shared by all groups
+  int n_per_group;
+  long long w_group_floats;   // floats between the prepared weights of consecutive slots
+  int bias_group_floats;      // floats between the bias vectors of consecutive slots
+  int x_shared, res_shared;   // 1: the input / residual has n_per_group images, read by every group
+  unsigned char gslot[8];
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------
@@ -207,7 +214,11 @@ conv_tc_kernel(ConvTcArgs a) {
   const int strips = (a.W + TC_M - 1) / TC_M;
   const int x0 = (blockIdx.x % strips) * TC_M;
   const int y0 = (blockIdx.x / strips) * R;
-  const int n = blockIdx.y;
+  const int n = blockIdx.y;                                  // image of the (grouped) output, mask and bias-table tensors
+  const int grp = n / a.n_per_group, nl = n - grp * a.n_per_group;
+  const int slot = a.gslot[grp & 7];
+  const int n_x = a.x_shared ? nl : n, n_res = a.res_shared ? nl : n;
+  const float* __restrict__ wprep = a.wprep + (long long)slot * a.w_group_floats;
   const bool relu_in = (a.flags & RISP_CONV_RELU_IN) != 0;
 #ifdef RISP_TC_TRACE
   const bool trace_cta = blockIdx.x == 5 && blockIdx.y == 0;
@@ -225,7 +236,7 @@ conv_tc_kernel(ConvTcArgs a) {
 #pragma unroll
     for (int i = 0; i < 2 * NBUF + 2; ++i) mbar_init(smem_u32(mbar + i), 1);
   }
-  if (tid >= 64 && tid < 128) s_bias[tid - 64] = (a.bias && tid - 64 < a.Cout) ? __ldg(a.bias + tid - 64) : 0.f;
+  if (tid >= 64 && tid < 128) s_bias[tid - 64] = (a.bias && tid - 64 < a.Cout) ? __ldg(a.bias + slot * a.bias_group_floats + tid - 64) : 0.f;
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   tc_fence_before();
   __syncthreads();
@@ -235,7 +246,7 @@ conv_tc_kernel(ConvTcArgs a) {
   const int n_chunks = (a.Cin + CI_C - 1) / CI_C;
   const int n_stages = n_chunks * C::NST;
   const long long row_stride = (long long)a.CinG * a.W * 4;              // floats per image row (blocked layout)
-  const float* xin = a.x + (long long)n * a.H * row_stride;
+  const float* xin = a.x + (long long)n_x * a.H * row_stride;
   const float* min_ = a.mask_in ? a.mask_in + (long long)n * a.H * row_stride : nullptr;
   const long long lo_off = (long long)a.w_chunks * C::B_CHUNK_FLOATS;
   constexpr uint32_t kStageBytes = C::B_STAGE_FLOATS * 4;
@@ -247,8 +258,8 @@ conv_tc_kernel(ConvTcArgs a) {
     const uint32_t bar = bfull + 8u * b;
     const uint32_t dst = smem_u32(sB) + b * 2u * kStageBytes;
     mbar_expect_tx(bar, 2u * kStageBytes);
-    bulk_g2s(dst, a.wprep + off, kStageBytes, bar);
-    bulk_g2s(dst + kStageBytes, a.wprep + lo_off + off, kStageBytes, bar);
+    bulk_g2s(dst, wprep + off, kStageBytes, bar);
+    bulk_g2s(dst + kStageBytes, wprep + lo_off + off, kStageBytes, bar);
   };
 
   // input rows of chunk c -> registers (zero padding; the optional mask is applied here so only one array stays live).
@@ -475,7 +486,7 @@ conv_tc_kernel(ConvTcArgs a) {
     const bool ok = gy < a.H && gx < a.W;
     const long long rb = img_base + (long long)gy * orow;
     float* yrow = a.y_blk + rb;
-    const float* rrow = a.res + rb;                     // only dereferenced when the pointer is set
+    const float* rrow = a.res + rb + (long long)(n_res - n) * a.H * orow;      // only dereferenced when the pointer is set
     const float* mrow = a.mask_out + rb;
     const int gyc = gy < a.H ? gy : a.H - 1;
     const int ycls = gyc < C::PAD ? gyc : (gyc >= a.H - C::PAD ? K - (a.H - gyc) : C::PAD);
@@ -736,10 +747,14 @@ extern "C" int risp_from_blocked(const float* blocked, float* planar, int N, int
 // F = 9 + P <= 32 features, J = K*K*CoutPad (5184 for SRCNNRes); S is constant.  Two trivial kernels instead of cuBLAS's
 // gemv (which needs ~85 us for this shape) / an elementwise product + row sums.
 namespace risp {
+struct GroupSlots { unsigned char s[8]; };
 __global__ void __launch_bounds__(256)
 bias_table_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ S, const float* __restrict__ b, float* __restrict__ tab,
-                      int F, int J) {
+                      int F, int J, int n_per_group, GroupSlots gs) {
   const int n = blockIdx.y;
+  const int slot = gs.s[(n / n_per_group) & 7];
+  S += (long long)slot * F * J;
+  b += (long long)slot * J;
   __shared__ float f_s[32];
   if (threadIdx.x < F) f_s[threadIdx.x] = feat[n * F + threadIdx.x];
   __syncthreads();
@@ -750,8 +765,10 @@ bias_table_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ 
   }
 }
 __global__ void __launch_bounds__(256)
-bias_table_bwd_kernel(const float* __restrict__ dtab, const float* __restrict__ S, float* __restrict__ dfeat, int F, int J) {
+bias_table_bwd_kernel(const float* __restrict__ dtab, const float* __restrict__ S, float* __restrict__ dfeat, int F, int J,
+                      int n_per_group, GroupSlots gs) {
   const int f = blockIdx.x, n = blockIdx.y;                  // one CTA per output element, fixed summation order
+  S += (long long)gs.s[(n / n_per_group) & 7] * F * J;
   float acc = 0.f;
   for (int j = threadIdx.x; j < J; j += 256) acc = fmaf(dtab[(long long)n * J + j], __ldg(S + (long long)f * J + j), acc);
   __shared__ float red[8];
@@ -766,18 +783,49 @@ bias_table_bwd_kernel(const float* __restrict__ dtab, const float* __restrict__ 
 }
 }  // namespace risp
 
-extern "C" int risp_bias_table_fwd(const float* feat, const float* S, const float* b, float* tab, int N, int F, int J,
-                                   risp_stream_t stream) {
-  RISP_REQUIRE(feat && S && b && tab && N > 0 && N <= 65535 && F >= 1 && F <= 32 && J >= 1, RISP_E_INVALID, "risp_bias_table_fwd: bad arguments");
+static int make_group_slots(risp::GroupSlots* gs, int G, const int* slots, const char* who) {
+  RISP_REQUIRE(G >= 1 && G <= 8 && slots, RISP_E_INVALID, "%s: 1..8 groups", who);
+  for (int g = 0; g < 8; ++g) gs->s[g] = 0;
+  for (int g = 0; g < G; ++g) {
+    RISP_REQUIRE(slots[g] >= 0 && slots[g] < 256, RISP_E_INVALID, "%s: slot out of range", who);
+    gs->s[g] = (unsigned char)slots[g];
+  }
+  return RISP_OK;
+}
+
+// grouped: feat / tab / dtab / dfeat have G*N rows; group g uses S + slots[g]*F*J and b + slots[g]*J
+extern "C" int risp_bias_table_fwd_grouped(const float* feat, const float* S, const float* b, float* tab, int G, int N_per_group,
+                                           const int* slots, int F, int J, risp_stream_t stream) {
+  risp::GroupSlots gs;
+  int rc = make_group_slots(&gs, G, slots, "risp_bias_table_fwd");
+  if (rc != RISP_OK) return rc;
+  const int N = G * N_per_group;
+  RISP_REQUIRE(feat && S && b && tab && N_per_group > 0 && N <= 65535 && F >= 1 && F <= 32 && J >= 1, RISP_E_INVALID, "risp_bias_table_fwd: bad arguments");
   const int bx = (int)(cdiv(J, 256) > 64 ? 64 : cdiv(J, 256));
-  risp::bias_table_fwd_kernel<<<dim3((unsigned)bx, (unsigned)N), 256, 0, as_stream(stream)>>>(feat, S, b, tab, F, J);
+  risp::bias_table_fwd_kernel<<<dim3((unsigned)bx, (unsigned)N), 256, 0, as_stream(stream)>>>(feat, S, b, tab, F, J, N_per_group, gs);
   return check_launch("bias_table_fwd_kernel");
 }
 
-extern "C" int risp_bias_table_bwd(const float* dtab, const float* S, float* dfeat, int N, int F, int J, risp_stream_t stream) {
-  RISP_REQUIRE(dtab && S && dfeat && N > 0 && N <= 65535 && F >= 1 && F <= 32 && J >= 1, RISP_E_INVALID, "risp_bias_table_bwd: bad arguments");
-  risp::bias_table_bwd_kernel<<<dim3((unsigned)F, (unsigned)N), 256, 0, as_stream(stream)>>>(dtab, S, dfeat, F, J);
+extern "C" int risp_bias_table_bwd_grouped(const float* dtab, const float* S, float* dfeat, int G, int N_per_group, const int* slots,
+                                           int F, int J, risp_stream_t stream) {
+  risp::GroupSlots gs;
+  int rc = make_group_slots(&gs, G, slots, "risp_bias_table_bwd");
+  if (rc != RISP_OK) return rc;
+  const int N = G * N_per_group;
+  RISP_REQUIRE(dtab && S && dfeat && N_per_group > 0 && N <= 65535 && F >= 1 && F <= 32 && J >= 1, RISP_E_INVALID, "risp_bias_table_bwd: bad arguments");
+  risp::bias_table_bwd_kernel<<<dim3((unsigned)F, (unsigned)N), 256, 0, as_stream(stream)>>>(dtab, S, dfeat, F, J, N_per_group, gs);
   return check_launch("bias_table_bwd_kernel");
+}
+
+extern "C" int risp_bias_table_fwd(const float* feat, const float* S, const float* b, float* tab, int N, int F, int J,
+                                   risp_stream_t stream) {
+  const int slot0 = 0;
+  return risp_bias_table_fwd_grouped(feat, S, b, tab, 1, N, &slot0, F, J, stream);
+}
+
+extern "C" int risp_bias_table_bwd(const float* dtab, const float* S, float* dfeat, int N, int F, int J, risp_stream_t stream) {
+  const int slot0 = 0;
+  return risp_bias_table_bwd_grouped(dtab, S, dfeat, 1, N, &slot0, F, J, stream);
 }
 
 extern "C" size_t risp_blocked_class_sums_workspace(int N, int C, int H, int K) {
@@ -810,6 +858,21 @@ extern "C" int risp_conv_tc_fwd(const float* x_blk, const float* mask_in_blk, co
 extern "C" int risp_conv_tc_fwd_tab(const float* x_blk, const float* mask_in_blk, const float* wprep, const float* bias,
                                     const float* bias_tab, const float* res_blk, const float* mask_out_blk, float* y_blk,
                                     float* y_planar, int N, int Cin, int Cout, int H, int W, int K, int flags, risp_stream_t stream) {
+  const int slot0 = 0;
+  return risp_conv_tc_fwd_grouped(x_blk, mask_in_blk, wprep, bias, bias_tab, res_blk, mask_out_blk, y_blk, y_planar, 1, N, &slot0, 0, 0,
+                                  0, 0, Cin, Cout, H, W, K, flags, stream);
+}
+
+// G groups x N images per group in ONE launch: the output, the masks and the bias table have G*N images; group g multiplies
+// by the prepared weights at wprep + slots[g] * w_group_floats (bias at bias + slots[g] * bias_group_floats); the input /
+// residual have N images when x_shared / res_shared is set (every group reads the same images), else G*N.
+extern "C" int risp_conv_tc_fwd_grouped(const float* x_blk, const float* mask_in_blk, const float* wprep, const float* bias,
+                                        const float* bias_tab, const float* res_blk, const float* mask_out_blk, float* y_blk,
+                                        float* y_planar, int G, int N_per_group, const int* slots, long long w_group_floats,
+                                        int bias_group_floats, int x_shared, int res_shared, int Cin, int Cout, int H, int W,
+                                        int K, int flags, risp_stream_t stream) {
+  RISP_REQUIRE(G >= 1 && G <= 8 && N_per_group >= 1 && slots, RISP_E_INVALID, "risp_conv_tc_fwd_grouped: 1..8 groups");
+  const int N = G * N_per_group;
   RISP_REQUIRE(x_blk && wprep && y_blk && N > 0 && H > 0 && W > 0 && N <= 65535, RISP_E_INVALID,
                "risp_conv_tc_fwd: bad arguments (the blocked output is required; the planar one is an optional copy)");
   RISP_REQUIRE(!bias_tab || (H >= K - 1 && W >= K - 1 && aligned16(bias_tab)), RISP_E_INVALID,
@@ -818,7 +881,12 @@ extern "C" int risp_conv_tc_fwd_tab(const float* x_blk, const float* mask_in_blk
   RISP_REQUIRE(!(flags & RISP_CONV_ADD_RES) || res_blk, RISP_E_INVALID, "risp_conv_tc_fwd: ADD_RES without a residual");
   const int NP = (Cout + 15) / 16 * 16;
   ConvTcArgs a{x_blk, wprep, bias, bias_tab, res_blk, mask_in_blk, mask_out_blk, y_blk, y_planar, risp_conv_tc_padded_channels(Cin) / 4,
-               Cout, NP, H, W, flags, Cin, ((Cin + 15) / 16 * 16 + tc_chunk(K) - 1) / tc_chunk(K)};
+               Cout, NP, H, W, flags, Cin, ((Cin + 15) / 16 * 16 + tc_chunk(K) - 1) / tc_chunk(K),
+               N_per_group, w_group_floats, bias_group_floats, x_shared, res_shared, {0, 0, 0, 0, 0, 0, 0, 0}};
+  for (int g = 0; g < G; ++g) {
+    RISP_REQUIRE(slots[g] >= 0 && slots[g] < 256, RISP_E_INVALID, "risp_conv_tc_fwd_grouped: slot out of range");
+    a.gslot[g] = (unsigned char)slots[g];
+  }
   cudaStream_t st = as_stream(stream);
   const int rc = conv_tc_dispatch(a, N, K, NP, st);
   if (rc != RISP_OK || !y_planar) return rc;

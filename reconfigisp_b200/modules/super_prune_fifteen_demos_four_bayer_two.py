@@ -106,6 +106,7 @@ class SuperPruneFifteenDemosFourBayerTwo(nn.Module):
         # of named_parameters()/state_dict()/DDP
         self._chain = ops.Chain([op for _, op in SRGB_CLASSICAL])
         self.n_streams = int(os.environ.get('RISP_SEARCH_STREAMS', '4'))
+        self.use_bank = os.environ.get('RISP_SRCNN_BANK', '1') != '0'
         self._streams = []
 
     def _apply(self, fn, *a, **k):
@@ -118,12 +119,12 @@ class SuperPruneFifteenDemosFourBayerTwo(nn.Module):
     def _post_probs(self):
         """post-prune weights of every step (device, differentiable) + one host copy for control flow."""
         posts = [ops.alpha_prune(a, self.threshold) for a in self.all_alphas]
-        host = torch.cat([p.detach() for p in posts]).cpu()
+        host = torch.cat([p.detach() for p in posts]).cpu().tolist()      # plain floats: the control flow below is pure Python
         out, o = [], 0
         for i, p in enumerate(posts):
             h = host[o:o + p.numel()]
             o += p.numel()
-            self.pruned_paths[i] = int((h == 0).sum())
+            self.pruned_paths[i] = sum(1 for v in h if v == 0)
             out.append((p, h))
         return out
 
@@ -160,8 +161,25 @@ class SuperPruneFifteenDemosFourBayerTwo(nn.Module):
         for s in self._streams[:n]:
             main.wait_stream(s)
         for o in outs:
-            o.record_stream(main)
+            for t in (o if isinstance(o, (list, tuple)) else (o,)):
+                t.record_stream(main)
         return outs
+
+    def _srcnn_bank(self, s, mods):
+        banks = self.__dict__.setdefault('_banks', {})
+        if s not in banks:
+            index = [i for i in range(15) if isinstance(mods[i], P.SRCNNRes)]
+            banks[s] = P.SRCNNResBank([mods[i] for i in index])
+            banks[s].index = index
+        return banks[s]
+
+    def _index(self, idx, device):
+        """device index tensor of a candidate list (cached: a Python list index costs a host->device copy every time)."""
+        cache = self.__dict__.setdefault('_idx_cache', {})
+        k = (tuple(idx), str(device))
+        if k not in cache:
+            cache[k] = torch.tensor(list(idx), dtype=torch.int64, device=device)
+        return cache[k]
 
     def _table_affine(self, device):
         """[0,1] -> kernel range of the classical candidates' parameters as one affine map over the 37 table entries."""
@@ -188,7 +206,7 @@ class SuperPruneFifteenDemosFourBayerTwo(nn.Module):
             widx.append(0)
         if host[1] < 1e-9:                                    # skip pruned: zero weight keeps the kernel generic
             pass
-        y = ops.mixed_op(x, ops.Chain(['skip']), None, post[widx], ext)
+        y = ops.mixed_op(x, ops.Chain(['skip']), None, post.index_select(0, self._index(widx, post.device)), ext)
         self.middle_results.append(y)
         x = y
 
@@ -202,7 +220,7 @@ class SuperPruneFifteenDemosFourBayerTwo(nn.Module):
             jobs.append(lambda k=k, x=x: mods[k](x, None))
             widx.append(k)
         ext = self._fan_out(jobs)
-        y = ops.mixed_op(ext[0].detach(), ops.Chain([]), None, post[widx], ext)
+        y = ops.mixed_op(ext[0].detach(), ops.Chain([]), None, post.index_select(0, self._index(widx, post.device)), ext)
         self.middle_results.append(y)
         x = y
 
@@ -227,18 +245,35 @@ class SuperPruneFifteenDemosFourBayerTwo(nn.Module):
             table = torch.cat([row[:, :1].expand(N, 1), gw, row[:, 1:].expand(N, 36)], dim=1)
             jobs, widx = [], list(cls_idx)
             pruned = [i for i in range(15) if host[i] < 1e-9]
+            # the SRCNNRes proxies of the step (same layer shapes once their constant channels are folded): one grouped job
+            bank = self._srcnn_bank(s, mods)
+            banked = [i for i in bank.index if not host[i] < 1e-9] if (self.use_bank and bank.usable(x)) else []
+            if len(banked) < 2:
+                banked = []
+            slot_of = {i: k for k, i in enumerate(bank.index)}
+            where = {}                                     # candidate index -> (job, position in the job's result list)
+            if banked:
+                where.update({i: (0, k) for k, i in enumerate(banked)})
+                jobs.append(lambda x=x, b=banked: bank(x, [sig(i) for i in b], [slot_of[i] for i in b]))
             for i in range(15):
                 if i in cls_idx or host[i] < 1e-9:
                     continue
+                widx.append(i)
+                if i in where:
+                    continue
                 par = pars[i]
                 par_tensor = None if par.nelement() == 0 else sig(i).expand(N, -1)
+                where[i] = (len(jobs), None)
                 jobs.append(lambda i=i, x=x, p=par_tensor: mods[i](x, p))
-                widx.append(i)
             if jobs:
                 P.prepare_shared(x)          # blocked copy + statistics of the stage input, once, on the main stream
-            ext = self._fan_out(jobs)
+            res = self._fan_out(jobs)
             P.release_shared(x)
-            w = post[widx]
+            ext = []
+            for i in widx[len(cls_idx):]:
+                j, k = where[i]
+                ext.append(res[j] if k is None else res[j][k])
+            w = post.index_select(0, self._index(widx, post.device))
             dummy = self._dummy(pars, pruned)
             if dummy is not None:
                 w = w + dummy

@@ -152,6 +152,62 @@ class SRCNNRes(nn.Module):
         return conv.from_blocked(h, 3)
 
 
+class SRCNNResBank:
+    """The SRCNNRes proxies of ONE supernet step evaluated together (`ops.srcnn_res_bank`): their prepared weights, folded
+    tables and biases stacked slot by slot, rebuilt when any weight changes.  Only for frozen members (the search path);
+    `usable()` says whether the grouped path applies to an input."""
+
+    def __init__(self, nets):
+        self.nets = list(nets)                       # slot order
+        self._cache = None
+        self._pidx = {}
+
+    def usable(self, x):
+        return (all(_frozen(n.srcnn[0], n.srcnn[2], n.srcnn[4]) for n in self.nets) and min(x.shape[2], x.shape[3]) >= 8
+                and len(self.nets) <= 8 and all(n.srcnn[0].weight.shape[0] == 64 for n in self.nets))
+
+    def bank(self):
+        key = tuple((c.weight._version, c.weight.data_ptr(), c.bias._version) for n in self.nets for c in (n.srcnn[0], n.srcnn[2], n.srcnn[4]))
+        if self._cache is None or self._cache[0] != key:
+            with torch.no_grad():
+                Ps = [n.srcnn[0].weight.shape[1] - 12 for n in self.nets]
+                Pmax = max(Ps)
+                F = 9 + Pmax
+                W1, W1T, W2, W2T, W3, W3T, S, BR, B2, B3 = ([] for _ in range(10))
+                for n in self.nets:
+                    c1, c2, c3 = n.srcnn[0], n.srcnn[2], n.srcnn[4]
+                    w_img, S_n, b_rep = n._folded()
+                    W1.append(ops._tc_weights(w_img, False)); W1T.append(ops._tc_weights(w_img, True))
+                    W2.append(ops._tc_weights(c2.weight, False)); W2T.append(ops._tc_weights(c2.weight, True))
+                    W3.append(ops._tc_weights(c3.weight, False)); W3T.append(ops._tc_weights(c3.weight, True))
+                    Sp = torch.zeros((F, S_n.shape[1]), device=S_n.device, dtype=torch.float32)
+                    Sp[:S_n.shape[0]] = S_n
+                    S.append(Sp); BR.append(b_rep)
+                    B2.append(c2.bias.detach().float()); B3.append(c3.bias.detach().float())
+                st = lambda l: torch.stack(l).contiguous()
+                d = dict(W1=st(W1), W1T=st(W1T), W2=st(W2), W2T=st(W2T), W3=st(W3), W3T=st(W3T), S=st(S), BR=st(BR), B2=st(B2), B3=st(B3),
+                         Ps=Ps, Pmax=Pmax, F=F, J=int(S[0].shape[1]), par_index=self._par_index)
+            if torch.cuda.is_available():
+                torch.cuda.current_stream().synchronize()
+            self._cache = (key, d)
+            self._pidx = {}
+        return self._cache[1]
+
+    def _par_index(self, active, device):
+        k = (active, str(device))
+        if k not in self._pidx:
+            d = self._cache[1]
+            idx = [g * d['Pmax'] + j for g, slot in enumerate(active) for j in range(d['Ps'][slot])]
+            self._pidx[k] = torch.tensor(idx, dtype=torch.int64, device=device)
+        return self._pidx[k]
+
+    def __call__(self, x, pars, active):
+        """x (N,3,H,W); pars: list of (1, P_slot) tensors in [0,1] for the active slots -> list of G outputs (N,3,H,W)."""
+        y = ops.srcnn_res_bank(x, torch.cat(pars, dim=1), self.bank(), list(active))
+        N = x.shape[0]
+        return list(y.view(len(active), N, *y.shape[1:]).unbind(0))
+
+
 class SRCNNDemosaic(nn.Module):
     """srcnn_demosaic_arch.py:6-55: RGGB pack -> conv9-ReLU-conv1-ReLU-conv5 -> PixelShuffle(2)."""
 

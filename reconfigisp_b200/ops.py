@@ -1011,6 +1011,89 @@ def resblock_tc(xb, w1, b1, w2, b2):
     return _ResBlockTcFn.apply(xb, w1, b1, w2, b2)
 
 
+# ---- a bank of SRCNNRes proxies evaluated together (grouped launches) ---------------------------------------------------------
+def _gconv(xb, mask_in, W, bias, bias_stride, tab, resb, G, N, slots, x_shared, res_shared, Cin, Cout, K, flags):
+    """one grouped tensor-core convolution: G*N output images; W (n_slots, floats) prepared weights of every bank member"""
+    H, Wd = xb.shape[1], xb.shape[3]
+    yb = torch.empty((G * N, H, tc_groups(Cout), Wd, 4), device=xb.device, dtype=torch.float32)
+    L.call('risp_conv_tc_fwd_grouped', L.ptr(xb), L.ptr(mask_in), L.ptr(W), L.ptr(bias), L.ptr(tab), L.ptr(resb), None, L.ptr(yb), None,
+           G, N, slots, W.shape[1], int(bias_stride), int(x_shared), int(res_shared), Cin, Cout, H, Wd, K, int(flags), L.stream())
+    return yb
+
+
+class _SRCNNResBankFn(torch.autograd.Function):
+    """y_g = SRCNNRes_g(x, p_g) for the G active members of a bank (same x, different weights and parameters):
+    (N,3,H,W), (1, sum P_g) -> (G*N, 3, H, W).  Every layer is ONE grouped launch (the members have identical layer shapes
+    once the constant channels are folded into the bias table), forward and backward; the statistics, the blocked copy of
+    x and the gradient paths into x (data gradient of the first layer, residual, min/mean/max routing) are shared.
+    At the reference's 4 x 256^2 batch a single member's layer is 1.7-3.5 waves of CTAs; eight together are 14-28."""
+
+    @staticmethod
+    def forward(ctx, x, par_cat, bank, active):
+        x = _img(x, 3)
+        N, _, H, Wd = x.shape
+        G = len(active)
+        slots = L.iarr(active)
+        dev = x.device
+        xb = torch.empty((N, H, 1, Wd, 4), device=dev, dtype=torch.float32)
+        L.call('risp_to_blocked', L.ptr(x), L.ptr(xb), N, 3, 1, H, Wd, L.stream())
+        st = plane_stats(x)                                             # (N,3,3) [min, mean, max] per plane
+        idx = torch.empty((N * 3, 2), device=dev, dtype=torch.int32)
+        L.call('risp_plane_argfirst', L.ptr(x), L.ptr(st), L.ptr(idx), N * 3, H * Wd, L.stream())
+        st9 = st.permute(0, 2, 1).reshape(N, 9)
+        Pmax, F, J = bank['Pmax'], bank['F'], bank['J']
+        pidx = bank['par_index'](tuple(active), dev)                      # where every active parameter lands in (G, Pmax)
+        par_pad = torch.zeros((G * Pmax,), device=dev, dtype=torch.float32).index_copy_(0, pidx, par_cat.detach().reshape(-1).float())
+        feat = torch.cat([st9.unsqueeze(0).expand(G, N, 9), par_pad.view(G, 1, Pmax).expand(G, N, Pmax)], dim=2).contiguous()
+        tab = torch.empty((G * N, J), device=dev, dtype=torch.float32)
+        L.call('risp_bias_table_fwd_grouped', L.ptr(feat), L.ptr(bank['S']), L.ptr(bank['BR']), L.ptr(tab), G, N, slots, F, J, L.stream())
+        h1 = _gconv(xb, None, bank['W1'], None, 0, tab, None, G, N, slots, 1, 0, 3, 64, 9, CONV_RELU_OUT)
+        h2 = _gconv(h1, None, bank['W2'], bank['B2'], 32, None, None, G, N, slots, 0, 0, 64, 32, 5, CONV_RELU_OUT)
+        yb = _gconv(h2, None, bank['W3'], bank['B3'], 3, None, xb, G, N, slots, 0, 1, 32, 3, 5, CONV_ADD_RES)
+        y = torch.empty((G * N, 3, H, Wd), device=dev, dtype=torch.float32)
+        L.call('risp_from_blocked', L.ptr(yb), L.ptr(y), G * N, 3, 1, H, Wd, L.stream())
+        ctx.save_for_backward(h1, h2, idx, pidx)
+        ctx.bank, ctx.active, ctx.shape = bank, list(active), (N, H, Wd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        h1, h2, idx, pidx = ctx.saved_tensors
+        bank, active = ctx.bank, ctx.active
+        N, H, Wd = ctx.shape
+        G = len(active)
+        slots = L.iarr(active)
+        dev = dy.device
+        dy = dy.contiguous()
+        dyb = torch.empty((G * N, H, 1, Wd, 4), device=dev, dtype=torch.float32)
+        L.call('risp_to_blocked', L.ptr(dy), L.ptr(dyb), G * N, 3, 1, H, Wd, L.stream())
+        dh2 = _gconv(dyb, None, bank['W3T'], None, 0, None, None, G, N, slots, 0, 0, 3, 32, 5, 0)
+        dh1 = _gconv(dh2, h2, bank['W2T'], None, 0, None, None, G, N, slots, 0, 0, 32, 64, 5, 0)
+        dxg = _gconv(dh1, h1, bank['W1T'], None, 0, None, None, G, N, slots, 0, 0, 64, 3, 9, 0)
+        Pmax, F, J = bank['Pmax'], bank['F'], bank['J']
+        dtab = blocked_class_sums(dh1, h1, 64, 9).view(G * N, J)
+        dfeat = torch.empty((G * N, F), device=dev, dtype=torch.float32)
+        L.call('risp_bias_table_bwd_grouped', L.ptr(dtab), L.ptr(bank['S']), L.ptr(dfeat), G, N, slots, F, J, L.stream())
+        dfeat = dfeat.view(G, N, F)
+        dpar = dfeat[:, :, 9:].sum(dim=1).reshape(-1).index_select(0, pidx).view(1, -1) if ctx.needs_input_grad[1] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dst = dfeat[:, :, :9].sum(dim=0)                                         # (N, 9) = d [min | mean | max]
+            gp = dst.reshape(N, 3, 3).permute(0, 2, 1).contiguous()                  # (N, C, 3) like the statistics
+            dx = torch.empty((N, 3, H, Wd), device=dev, dtype=torch.float32)
+            L.call('risp_plane_stats_bwd', L.ptr(gp), L.ptr(idx), L.ptr(dx), N * 3, H * Wd, L.stream())
+            # first-layer data gradients + the residual path of every member, summed over the bank
+            dxb = (dxg + dyb).view(G, N, H, 1, Wd, 4).sum(dim=0)
+            dxp = torch.empty((N, 3, H, Wd), device=dev, dtype=torch.float32)
+            L.call('risp_from_blocked', L.ptr(dxb), L.ptr(dxp), N, 3, 1, H, Wd, L.stream())
+            dx += dxp
+        return dx, dpar, None, None
+
+
+def srcnn_res_bank(x, par_cat, bank, active):
+    return _SRCNNResBankFn.apply(x, par_cat, bank, active)
+
+
 def conv2d_tc(xb, weight, bias=None, relu_in=False, relu_out=False, residual=None, residual_relu=False, bias_tab=None):
     """Blocked in, blocked out.  bias_tab (N, K*K*pad16(Cout)): differentiable position-class bias (instead of `bias`)."""
     return _ConvTcFn.apply(xb, residual, weight, bias, relu_in, relu_out, residual_relu, bias_tab)

@@ -383,3 +383,36 @@ def test_srcnn_res_folded_constant_channels_match_materialised(P_, shape):
     assert maxabs(yf, ym) <= 2e-5 * max(1.0, float(ym.detach().abs().max())), (maxabs(yf, ym), float(ym.detach().abs().max()))
     relclose_relu_net(dxf, dxm, rtol=1e-4, flip_frac=2e-2)
     relclose(dpf, dpm, rtol=2e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize('active', [list(range(8)), [0, 3, 7], [5, 2]])
+def test_srcnn_res_bank_matches_individual_proxies(active):
+    """The grouped evaluation of a step's SRCNNRes proxies (one launch per layer for all members, shared statistics and input
+    gradient paths) against the members evaluated one by one: outputs, d x and every parameter gradient."""
+    from reconfigisp_b200.modules import tools_proxy as P
+    g = torch.Generator().manual_seed(5)
+    Ps = [2, 1, 2, 1, 3, 1, 3, 5]                      # reinhard, crysis, filmic, whiteworld, bilateral, median, fastnlm, bm3d
+    nets = []
+    for k, p_ in enumerate(Ps):
+        net = P.ProxyNet(p_, None)
+        net.load_state_dict(P.seeded_state_dict(net, 40 + k))
+        nets.append(net.cuda().requires_grad_(False))
+    N, H, W = 2, 37, 150
+    x0 = torch.rand(N, 3, H, W, generator=g).clamp(0.1, 0.9).cuda()
+    p0 = [torch.rand(1, Ps[s], generator=g).cuda() for s in active]
+    dys = [torch.randn(N, 3, H, W, generator=g).cuda() for _ in active]
+    bank = P.SRCNNResBank(nets)
+    assert bank.usable(x0)
+    x = x0.clone().requires_grad_()
+    ps = [p.clone().requires_grad_() for p in p0]
+    ys = bank(x, ps, active)
+    got = torch.autograd.grad(ys, [x] + ps, dys)
+    xr = x0.clone().requires_grad_()
+    pr = [p.clone().requires_grad_() for p in p0]
+    yr = [nets[s](xr, q.expand(N, -1)) for s, q in zip(active, pr)]
+    ref = torch.autograd.grad(yr, [xr] + pr, dys)
+    for a, b in zip(ys, yr):
+        assert maxabs(a, b.detach()) <= 2e-5 * max(1.0, float(b.detach().abs().max()))
+    relclose_relu_net(got[0], ref[0], rtol=1e-4, flip_frac=2e-2)
+    for a, b in zip(got[1:], ref[1:]):
+        relclose(a, b, rtol=2e-3, atol=1e-5)
