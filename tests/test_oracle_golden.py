@@ -177,3 +177,41 @@ def test_darts_step_against_reference_model(golden):
     assert len(nz) == int(g['n_params'])
     for i, gr in enumerate(grads):
         close(torch.zeros_like(nz[i]) if gr is None else gr, g['it0_param_grad_%d' % i], 2e-6)
+
+
+def _summary(t):
+    f = t.detach().reshape(-1).double()
+    head = f[:24].float() if f.numel() >= 24 else torch.nn.functional.pad(f.float(), (0, 24 - f.numel()))
+    return torch.cat([head, torch.tensor([float(f.sum()), float(f.abs().sum())])])
+
+
+def test_finetune_step_against_reference_model(golden):
+    """The oracle's proxy / target / loss pieces replayed with the reference's host RNG draws against a run of the
+    reference's own `DartsFtModel.finetune_proxies` (oracle/gen_golden_darts_ft.py): first-step loss and weight gradients of
+    every flagged proxy.  The FIFO holds the sRGB intermediates of the training pass (darts_ft_model.py:194-201)."""
+    import random
+    g = golden('darts_ft')
+    names = [str(n) for n in g['names']]
+    assert names == ['crysisengine', 'whiteworld', 'bilateral', 'median', 'fastnlm']
+    oG = PO.Supernet(3, 0.2, 10)
+    y, mids = oG.forward(T(g['img']))
+    assert abs(float(((y - T(g['gt'])) ** 2).mean().detach()) - float(g['loss_G'])) <= 1e-6
+    mem = [t.detach() for t in mids if t.shape[1] == 3]
+    assert len(mem) == int(g['n_ft_data'])
+    step_names = [n for n, _ in PO.SRGB_STEP]
+    random.seed(int(g['ft_seed'])); torch.manual_seed(int(g['ft_seed']))
+    for k, name in enumerate(names):
+        net = oG.steps[-1][step_names.index(name)]
+        data = mem[int(random.random() * len(mem))]
+        param = torch.rand(1, net.P).repeat(data.shape[0], 1)
+        sd = {kk: v.clone().requires_grad_() for kk, v in net.sd.items()}
+        loss = O.mse(O.srcnn_res(data, param, sd), PO.ORIGIN[name](data, param))
+        assert abs(float(loss.detach()) - float(g['losses'][k, 0])) <= 2e-6 * max(1.0, float(g['losses'][k, 0])), name
+        grads = torch.autograd.grad(loss, list(sd.values()))
+        ref = T(g['grads_' + name])[0]
+        for i, gr in enumerate(grads):
+            sm, rf = _summary(gr), ref[i].numpy()
+            close(sm[:24], rf[:24], 2e-5 * max(1e-3, float(np.abs(rf[:24]).max())))       # first values of the tensor
+            close(sm[24:], rf[24:], 2e-5 * max(1e-3, float(rf[25])))                        # its sum and abs-sum
+        # consume the second step's draws so that the next proxy sees the generator state the reference saw
+        int(random.random() * len(mem)); torch.rand(1, net.P)

@@ -180,3 +180,53 @@ def test_darts_model_matches_reference_run(golden):
         for i, p in enumerate(nz):
             relclose(p.grad, T(g['it%d_param_grad_%d' % (it, i)]), rtol=5e-3, atol=2e-7)
             relclose(p, T(g['it%d_param_%d' % (it, i)]), rtol=1e-4, atol=1e-6)
+
+
+def test_finetune_proxies_matches_reference_run(golden):
+    """`search_ft.DartsFtModel`: one training pass (fills the FIFO) + `finetune_proxies()` with ft_steps = 2 against the golden
+    recorded from the reference's own `DartsFtModel` (oracle/gen_golden_darts_ft.py): training loss, the loss of BOTH
+    fine-tune steps of every flagged proxy (the second one sees the weights Adam produced from the first) and the first-step
+    weight / bias gradients (first 24 values, sum, abs-sum of every tensor) -- same host RNG draws as the reference."""
+    import random
+    from reconfigisp_b200.networks import create_model
+    g = golden('darts_ft')
+    T = torch.from_numpy
+    o = _opt_ft(3, ft_steps=2)
+    o['proxy_ft_params']['memory_size'] = 8
+    o['train']['lr_G'] = float(g['lr'])
+    m = create_model(o)
+    names = [str(n) for n in g['names']]
+    assert [n for n, *_ in m.ft_nets] == names
+    m.feed_data((T(g['img']), T(g['gt']), T(g['vimg']), T(g['vgt'])))
+    m.optimize_parameters()
+    assert abs(float(m.log_dict['loss'].detach()) - float(g['loss_G'])) <= 2e-5
+    assert len(m.ft_data) == int(g['n_ft_data'])
+    losses, grads = [], {n: [] for n in names}
+    loss_fn = m._loss
+    m._loss = lambda a, b: (losses.append(loss_fn(a, b)) or losses[-1])
+
+    def summary(t):
+        f = t.detach().reshape(-1).double().cpu()
+        head = f[:24].float() if f.numel() >= 24 else torch.nn.functional.pad(f.float(), (0, 24 - f.numel()))
+        return torch.cat([head, torch.tensor([float(f.sum()), float(f.abs().sum())])])
+    for name, proxy, _, optim in m.ft_nets:
+        orig = optim.step
+
+        def step(orig=orig, proxy=proxy, name=name):
+            grads[name].append(torch.stack([summary(p.grad) for p in proxy.parameters()]))
+            return orig()
+        optim.step = step
+    random.seed(int(g['ft_seed'])); torch.manual_seed(int(g['ft_seed']))
+    m.finetune_proxies()
+    got = torch.stack([l.detach().cpu() for l in losses]).view(len(names), 2)
+    ref = T(g['losses'])
+    for k, name in enumerate(names):
+        assert abs(float(got[k, 0]) - float(ref[k, 0])) <= 2e-5 * max(1.0, float(ref[k, 0])), (name, float(got[k, 0]), float(ref[k, 0]))
+        # step 2 runs on Adam-updated weights: every weight moved by ~lr with the SIGN of its gradient, which is fragile for
+        # near-zero gradients, so the bar is relative
+        assert abs(float(got[k, 1]) - float(ref[k, 1])) <= 2e-2 * float(ref[k, 1]), (name, float(got[k, 1]), float(ref[k, 1]))
+        rg = T(g['grads_' + name])[0]
+        for i in range(rg.shape[0]):
+            a, b = grads[name][0][i], rg[i]
+            assert float((a[:24] - b[:24]).abs().max()) <= 3e-3 * max(1e-6, float(b[:24].abs().max())), (name, i)
+            assert abs(float(a[25]) - float(b[25])) <= 3e-3 * float(b[25]) + 1e-7, (name, i)
