@@ -79,6 +79,9 @@ __global__ void fused_prep_kernel(const float* __restrict__ params, int pstride,
         const bool in_range = (y1 >= 0.f && y1 <= 1.f) && (y2 >= 0.f && y2 <= 1.f) && (y3 >= 0.f && y3 <= 1.f);
         o[5] = in_range ? 0.f : 1.f;
         o[6] = 0.f; o[7] = 0.f;
+        // table form: out = s_k x + a_k on segment k, a_k = y_k - x_k s_k
+        o[8] = 0.f; o[9] = y1 - 0.25f * s1; o[10] = y2 - 0.5f * s2; o[11] = y3 - 0.75f * s3;
+        o[12] = s0; o[13] = s1; o[14] = s2; o[15] = s3;
       } break;
       default: break;
     }
@@ -162,17 +165,51 @@ struct RingCfg {
   static constexpr int GTB = (MODE == 0 /*MODE_FWD*/) ? 0 : 3 * GTPLANEB;  // [plane][row][128]
   static constexpr int RECB = RAWB + GTB;                                // multiple of 128
   static constexpr int WARPB = D * RECB;
-  static constexpr int SMEM = kWarps * WARPB + kWarps * D * 8 + 128;  // records + mbarriers + alignment slack
+  static constexpr int TBLOFF = (kWarps * WARPB + kWarps * D * 8 + 63) / 64 * 64;   // tone-curve tables (one per stage slot)
+  static constexpr int SMEM = TBLOFF + ((MODE == 0 /*MODE_FWD*/) ? 0 : RISP_MAX_STAGES * kGtmTableBytes) + 128;  // records + mbarriers + tables + alignment slack
 };
 
 __device__ __forceinline__ int reflect101(int r, int H) { return r < 0 ? -r : (r >= H ? 2 * H - 2 - r : r); }
 
 // ---- demosaic of the lane's 4 pixels; row parity is a template parameter (no selects) ---------------------------------
 // w[RO + j][i]: raw row r-HL+j, column c0-HL+i.  Sites: (even,even)=R (even,odd)=G1 (odd,even)=G2 (odd,odd)=B.
-template <int DM, int HL, int RO, bool ODD, int WRT>
+template <int DM, int HL, int RO, bool ODD, int WRT, bool PK>
 __device__ __forceinline__ void demosaic4(const float (&w)[WRT][4 + 2 * HL], float clip_hi, P2& lo, P2& hi) {
   float B[4], G[4], R[4];
   constexpr int M = RO + HL;     // window row of the pixel's own raw row
+#ifndef RISP_FUSED_NO_PACKED_DM
+  if constexpr (DM == RISP_DM_BILINEAR && PK) {   // PK: the chain starts with packed arithmetic on the pairs (gain / polynomial)
+    // The 0.5 / 0.25 / 1 weights are applied by ONE packed multiply per output pair (constant pair from the uniform
+    // datapath): a pair like (raw, 0.5*sum) then leaves the demosaic as the result of an arithmetic instruction.  A pair
+    // that is a plain pack of a raw window value and a computed value is re-packed by ptxas at every use (it
+    // rematerialises the two moves instead of keeping the 64-bit register live: 12 MOV per pixel in the step kernel).
+    // Same values bit for bit: x*1 is exact, the other products are the ones the scalar form computes.
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int x = HL + k;
+      const bool xo = (k & 1);
+      const float c = w[M][x];
+      if (ODD != xo) {   // green site
+        const float hor = w[M][x - 1] + w[M][x + 1], ver = w[M - 1][x] + w[M + 1][x];
+        G[k] = c;
+        if (!ODD) { R[k] = hor; B[k] = ver; } else { R[k] = ver; B[k] = hor; }
+      } else {
+        const float cross = (w[M - 1][x] + w[M + 1][x]) + (w[M][x - 1] + w[M][x + 1]);
+        const float diag = (w[M - 1][x - 1] + w[M - 1][x + 1]) + (w[M + 1][x - 1] + w[M + 1][x + 1]);
+        G[k] = cross;
+        if (!ODD) { R[k] = c; B[k] = diag; } else { R[k] = diag; B[k] = c; }
+      }
+    }
+    // weights of (even column, odd column): even rows R G / odd rows G B
+    const float2 sb = ODD ? make_float2(0.5f, 1.f) : make_float2(0.25f, 0.5f);
+    const float2 sg = ODD ? make_float2(1.f, 0.25f) : make_float2(0.25f, 1.f);
+    const float2 sr = ODD ? make_float2(0.5f, 0.25f) : make_float2(1.f, 0.5f);
+    lo.b = __fmul2_rn(make_float2(B[0], B[1]), sb); lo.g = __fmul2_rn(make_float2(G[0], G[1]), sg); lo.r = __fmul2_rn(make_float2(R[0], R[1]), sr);
+    hi.b = __fmul2_rn(make_float2(B[2], B[3]), sb); hi.g = __fmul2_rn(make_float2(G[2], G[3]), sg); hi.r = __fmul2_rn(make_float2(R[2], R[3]), sr);
+    (void)clip_hi;
+    return;
+  }
+#endif
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int x = HL + k;
@@ -229,11 +266,12 @@ __host__ __device__ constexpr bool per_channel_from(int k) {     // stages k.. n
 
 // stages K.. on ONE channel C of the pair (gamma / gain / tone curve): forward, loss term, backward.  Keeping a channel's
 // whole tail together makes its saved state transient (a few registers) instead of live across all three channels.
-template <unsigned SIG, int K, int MODE, int C>
+// NOMASK: stage K is a gamma whose clamp mask the caller merges with its own (see the polynomial's channel-major form)
+template <unsigned SIG, int K, int MODE, int C, bool NOMASK = false>
 struct Tail {
   static constexpr EffChain E = Eff<SIG>::e;
   static __device__ __forceinline__ float2 go(float2 x, float2 tgt, const float* __restrict__ cp, float2* acc, float2& loss,
-                                              float2& yout, bool slow, float lane_w) {
+                                              float2& yout, bool slow, float lane_w, uint32_t tbl) {
     if constexpr (K == E.n) {
       yout = x;
       if constexpr (MODE == MODE_BWD) return tgt;
@@ -253,23 +291,23 @@ struct Tail {
       const float* c = cp + E.coff[K];
       float2* a = acc + E.aoff[K];
       if constexpr (OP == RISP_OP_SKIP) {
-        return Tail<SIG, K + 1, MODE, C>::go(x, tgt, cp, acc, loss, yout, slow, lane_w);
+        return Tail<SIG, K + 1, MODE, C>::go(x, tgt, cp, acc, loss, yout, slow, lane_w, tbl);
       } else if constexpr (OP == RISP_OP_GAMMA) {
         float2 l2;
         const float gm = c[0];
         const float2 y = gamma_fwd2<IN01>(x, gm, l2);
-        const float2 d = Tail<SIG, K + 1, MODE, C>::go(y, tgt, cp, acc, loss, yout, slow, lane_w);
-        return gamma_bwd2<IN01, NEED_DX, true>(x, y, l2, d, gm, a[0]);
+        const float2 d = Tail<SIG, K + 1, MODE, C>::go(y, tgt, cp, acc, loss, yout, slow, lane_w, tbl);
+        return gamma_bwd2<IN01, NEED_DX, true, NOMASK>(x, y, l2, d, gm, a[0]);
       } else if constexpr (OP == RISP_OP_GAIN) {
         const float2 y = mul2s(x, c[C]);
-        const float2 d = Tail<SIG, K + 1, MODE, C>::go(y, tgt, cp, acc, loss, yout, slow, lane_w);
+        const float2 d = Tail<SIG, K + 1, MODE, C>::go(y, tgt, cp, acc, loss, yout, slow, lane_w, tbl);
         a[C] = fma2(d, x, a[C]);
         return NEED_DX ? mul2s(d, c[C]) : zero2();
       } else {
         static_assert(OP == RISP_OP_GTM && IN01, "packed path: unsupported per-channel op");
         float2 hd[3], m = zero2();
-        const float2 y = gtm_fwd2(x, c, hd, slow, m);
-        float2 d = Tail<SIG, K + 1, MODE, C>::go(y, tgt, cp, acc, loss, yout, slow, lane_w);
+        const float2 y = gtm_fwd2<kGtmTable>(x, c, hd, slow, m, tbl + K * kGtmTableBytes);
+        float2 d = Tail<SIG, K + 1, MODE, C>::go(y, tgt, cp, acc, loss, yout, slow, lane_w, tbl);
         if (slow) d = mul2(d, m);
         return gtm_bwd2<NEED_DX>(x, hd, d, c, a);
       }
@@ -281,12 +319,12 @@ template <unsigned SIG, int K, int MODE>
 struct Run {
   static constexpr EffChain E = Eff<SIG>::e;
   static __device__ __forceinline__ P2 go(const P2& x, const P2& tgt, const float* __restrict__ cp, float2* acc, float2& loss,
-                                          P2& yout, bool slow, float lane_w) {
+                                          P2& yout, bool slow, float lane_w, uint32_t tbl) {
     if constexpr (per_channel_from<SIG>(K)) {
       P2 d;
-      d.b = Tail<SIG, K, MODE, 0>::go(x.b, tgt.b, cp, acc, loss, yout.b, slow, lane_w);
-      d.g = Tail<SIG, K, MODE, 1>::go(x.g, tgt.g, cp, acc, loss, yout.g, slow, lane_w);
-      d.r = Tail<SIG, K, MODE, 2>::go(x.r, tgt.r, cp, acc, loss, yout.r, slow, lane_w);
+      d.b = Tail<SIG, K, MODE, 0>::go(x.b, tgt.b, cp, acc, loss, yout.b, slow, lane_w, tbl);
+      d.g = Tail<SIG, K, MODE, 1>::go(x.g, tgt.g, cp, acc, loss, yout.g, slow, lane_w, tbl);
+      d.r = Tail<SIG, K, MODE, 2>::go(x.r, tgt.r, cp, acc, loss, yout.r, slow, lane_w, tbl);
       return d;
     } else {
       constexpr int OP = E.op[K];
@@ -298,12 +336,12 @@ struct Run {
         GammaSaved sv;
         const float gm = c[0];
         const P2 y = gamma_fwd<IN01>(x, gm, sv);
-        const P2 d = Run<SIG, K + 1, MODE>::go(y, tgt, cp, acc, loss, yout, slow, lane_w);
+        const P2 d = Run<SIG, K + 1, MODE>::go(y, tgt, cp, acc, loss, yout, slow, lane_w, tbl);
         return gamma_bwd<IN01, NEED_DX, true>(sv, d, gm, a[0]);
       } else if constexpr (OP == RISP_OP_GAIN) {
         GainSaved sv;
         const P2 y = gain_fwd(x, c, sv);
-        const P2 d = Run<SIG, K + 1, MODE>::go(y, tgt, cp, acc, loss, yout, slow, lane_w);
+        const P2 d = Run<SIG, K + 1, MODE>::go(y, tgt, cp, acc, loss, yout, slow, lane_w, tbl);
         return gain_bwd<NEED_DX>(sv, d, c, a);
       } else if constexpr ((OP == RISP_OP_POLY10 || OP == FOP_POLYG) && !NEED_DX && per_channel_from<SIG>(K + 1)) {
         // channel-major: the monomials are the only cross-channel state; each output channel then runs its polynomial
@@ -318,8 +356,21 @@ struct Run {
 #pragma unroll
           for (int i = 1; i < 9; ++i) u = fma2s(c[C * 10 + i], phi[i], u);
           const float2 y = sat2(u);
-          const float2 d = Tail<SIG, K + 1, MODE, C>::go(y, tg, cp, acc, loss, yo, slow, lane_w);
-          const float2 e = sel2(u.x == y.x, u.y == y.y, d);     // clamp mask, inclusive: u in [0,1] <=> sat(u) == u
+#ifndef RISP_FUSED_NO_MERGED_MASK
+          // a gamma directly behind the polynomial masks its gradient with [y >= eps]; together with the clamp mask
+          // [0 <= u <= 1] that is [eps <= u <= 1] <=> max(sat(u), eps) == u: one compare on the value gamma computes anyway
+          constexpr bool GNEXT = (K + 1 < E.n) && (E.op[K + 1 < E.n ? K + 1 : K] == RISP_OP_GAMMA);
+#else
+          constexpr bool GNEXT = false;
+#endif
+          const float2 d = Tail<SIG, K + 1, MODE, C, GNEXT>::go(y, tg, cp, acc, loss, yo, slow, lane_w, tbl);
+          float2 e;
+          if constexpr (GNEXT) {
+            const float2 xc = make_float2(fmaxf(y.x, RISP_GAMMA_EPS), fmaxf(y.y, RISP_GAMMA_EPS));
+            e = sel2(xc.x == u.x, xc.y == u.y, d);
+          } else {
+            e = sel2(u.x == y.x, u.y == y.y, d);     // clamp mask, inclusive: u in [0,1] <=> sat(u) == u
+          }
 #pragma unroll
           for (int i = 0; i < 9; ++i) a[C * 10 + i] = fma2(e, phi[i], a[C * 10 + i]);
           a[C * 10 + 9] = add2(a[C * 10 + 9], e);
@@ -332,13 +383,13 @@ struct Run {
       } else if constexpr (OP == RISP_OP_POLY10 || OP == FOP_POLYG) {
         PolySaved sv;
         const P2 y = poly_fwd(x, c, sv);
-        const P2 d = Run<SIG, K + 1, MODE>::go(y, tgt, cp, acc, loss, yout, slow, lane_w);
+        const P2 d = Run<SIG, K + 1, MODE>::go(y, tgt, cp, acc, loss, yout, slow, lane_w, tbl);
         return poly_bwd<NEED_DX>(sv, d, c, a);
       } else {
         static_assert(OP == RISP_OP_GTM && IN01, "packed path: unsupported effective op");
         GtmSaved sv;
-        const P2 y = gtm_fwd(x, c, sv, slow);
-        const P2 d = Run<SIG, K + 1, MODE>::go(y, tgt, cp, acc, loss, yout, slow, lane_w);
+        const P2 y = gtm_fwd<kGtmTable>(x, c, sv, slow, tbl + K * kGtmTableBytes);
+        const P2 d = Run<SIG, K + 1, MODE>::go(y, tgt, cp, acc, loss, yout, slow, lane_w, tbl);
         return gtm_bwd<NEED_DX>(sv, d, c, a, slow);
       }
     }
@@ -348,7 +399,7 @@ struct Run {
 template <unsigned SIG, int K>
 struct Fwd {
   static constexpr EffChain E = Eff<SIG>::e;
-  static __device__ __forceinline__ P2 go(const P2& x, const float* __restrict__ cp, bool slow) {
+  static __device__ __forceinline__ P2 go(const P2& x, const float* __restrict__ cp, bool slow, uint32_t tbl) {
     if constexpr (K == E.n) {
       return x;
     } else {
@@ -360,8 +411,8 @@ struct Fwd {
       else if constexpr (OP == RISP_OP_GAMMA) { GammaSaved sv; y = gamma_fwd<IN01>(x, c[0], sv); }
       else if constexpr (OP == RISP_OP_GAIN) { GainSaved sv; y = gain_fwd(x, c, sv); }
       else if constexpr (OP == RISP_OP_POLY10 || OP == FOP_POLYG) { PolySaved sv; y = poly_fwd(x, c, sv); }
-      else { GtmSaved sv; y = gtm_fwd(x, c, sv, slow); }
-      return Fwd<SIG, K + 1>::go(y, cp, slow);
+      else { GtmSaved sv; y = gtm_fwd<false>(x, c, sv, slow, 0u); }
+      return Fwd<SIG, K + 1>::go(y, cp, slow, tbl);
     }
   }
 };
@@ -391,6 +442,7 @@ fused_kernel(FusedArgs a, ChainDesc d, const __grid_constant__ CUtensorMap tm_ra
   constexpr int WR = 2 * HL + 1, WC = 4 + 2 * HL;
   constexpr int NACC = (MODE == MODE_FWD || E.nacc == 0) ? 1 : E.nacc;
   constexpr int NCST = E.ncst > 0 ? E.ncst : 1;
+  constexpr bool PKDM = E.n > 0 && (E.op[0] == RISP_OP_POLY10 || E.op[0] == FOP_POLYG || E.op[0] == RISP_OP_GAIN);
   using RC = RingCfg<MODE>;
   constexpr int D = RC::D;
   extern __shared__ unsigned char smem_raw[];
@@ -413,10 +465,16 @@ fused_kernel(FusedArgs a, ChainDesc d, const __grid_constant__ CUtensorMap tm_ra
   // ---- ring set-up -------------------------------------------------------------------------------------------------
   const uint32_t ring = (smem_u32(smem_raw) + 127u) & ~127u;
   const uint32_t bars = ring + RC::WARPB;
+  const uint32_t tbl = ring + RC::TBLOFF;        // 64-byte aligned (the ring is 128-byte aligned)
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < D; ++s) mbar_init(bars + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if constexpr (kGtmTable && MODE != MODE_FWD) {
+#pragma unroll
+      for (int k = 0; k < E.n; ++k)
+        if (E.op[k] == RISP_OP_GTM) gtm_table_fill(tbl + k * kGtmTableBytes, cp + E.coff[k]);
+    }
   }
   __syncwarp();
   unsigned gcount = 0;        // records issued before the current item
@@ -499,11 +557,11 @@ fused_kernel(FusedArgs a, ChainDesc d, const __grid_constant__ CUtensorMap tm_ra
           }
         }
         P2 lo, hi;
-        demosaic4<DM, HL, 0, ODD, WR>(w, a.clip_hi, lo, hi);
+        demosaic4<DM, HL, 0, ODD, WR, PKDM>(w, a.clip_hi, lo, hi);
         P2 ylo, yhi;
         if constexpr (MODE == MODE_FWD) {
-          ylo = Fwd<SIG, 0>::go(lo, cp, slow);
-          yhi = Fwd<SIG, 0>::go(hi, cp, slow);
+          ylo = Fwd<SIG, 0>::go(lo, cp, slow, tbl);
+          yhi = Fwd<SIG, 0>::go(hi, cp, slow, tbl);
         } else {
           float4 tg[3];
   #pragma unroll
@@ -511,8 +569,8 @@ fused_kernel(FusedArgs a, ChainDesc d, const __grid_constant__ CUtensorMap tm_ra
           P2 tlo, thi;
           tlo.b = make_float2(tg[0].x, tg[0].y); tlo.g = make_float2(tg[1].x, tg[1].y); tlo.r = make_float2(tg[2].x, tg[2].y);
           thi.b = make_float2(tg[0].z, tg[0].w); thi.g = make_float2(tg[1].z, tg[1].w); thi.r = make_float2(tg[2].z, tg[2].w);
-          Run<SIG, 0, MODE>::go(lo, tlo, cp, acc, loss, ylo, slow, lane_w);
-          Run<SIG, 0, MODE>::go(hi, thi, cp, acc, loss, yhi, slow, lane_w);
+          Run<SIG, 0, MODE>::go(lo, tlo, cp, acc, loss, ylo, slow, lane_w, tbl);
+          Run<SIG, 0, MODE>::go(hi, thi, cp, acc, loss, yhi, slow, lane_w, tbl);
         }
         if ((MODE == MODE_FWD || yb) && active) {
           float* po = yb + (size_t)r * W + c0;
@@ -584,17 +642,17 @@ fused_kernel(FusedArgs a, ChainDesc d, const __grid_constant__ CUtensorMap tm_ra
         constexpr bool ODD = decltype(odd_tag)::value;
         P2 lo, hi;
         if constexpr (MODE == MODE_FWD) {
-          demosaic4<DM, HL, RO, ODD, WR + 1>(w, a.clip_hi, lo, hi);
+          demosaic4<DM, HL, RO, ODD, WR + 1, PKDM>(w, a.clip_hi, lo, hi);
         } else {                                     // register-heavy modes: a private window, dead before the chain starts
           float wl[WR][WC];
   #pragma unroll
           for (int j = 0; j < WR; ++j) load_row(wl[j], wa[j]);
-          demosaic4<DM, HL, 0, ODD, WR>(wl, a.clip_hi, lo, hi);
+          demosaic4<DM, HL, 0, ODD, WR, PKDM>(wl, a.clip_hi, lo, hi);
         }
         P2 ylo, yhi;
         if constexpr (MODE == MODE_FWD) {
-          ylo = Fwd<SIG, 0>::go(lo, cp, slow);
-          yhi = Fwd<SIG, 0>::go(hi, cp, slow);
+          ylo = Fwd<SIG, 0>::go(lo, cp, slow, tbl);
+          yhi = Fwd<SIG, 0>::go(hi, cp, slow, tbl);
         } else {
           float4 tg[3];
   #pragma unroll
@@ -602,8 +660,8 @@ fused_kernel(FusedArgs a, ChainDesc d, const __grid_constant__ CUtensorMap tm_ra
           P2 tlo, thi;
           tlo.b = make_float2(tg[0].x, tg[0].y); tlo.g = make_float2(tg[1].x, tg[1].y); tlo.r = make_float2(tg[2].x, tg[2].y);
           thi.b = make_float2(tg[0].z, tg[0].w); thi.g = make_float2(tg[1].z, tg[1].w); thi.r = make_float2(tg[2].z, tg[2].w);
-          Run<SIG, 0, MODE>::go(lo, tlo, cp, acc, loss, ylo, slow, lane_w);
-          Run<SIG, 0, MODE>::go(hi, thi, cp, acc, loss, yhi, slow, lane_w);
+          Run<SIG, 0, MODE>::go(lo, tlo, cp, acc, loss, ylo, slow, lane_w, tbl);
+          Run<SIG, 0, MODE>::go(hi, thi, cp, acc, loss, yhi, slow, lane_w, tbl);
         }
   #ifdef RISP_FUSED_DEBUG
         const bool st_ok = !(a.dbg & 1) || ylo.b.x == 12345.678f;

@@ -29,7 +29,7 @@ enum { FOP_POLYG = 12 };   // GAIN folded into POLY10; other effective ops reuse
 
 __host__ __device__ constexpr int fop_csize(int op) {   // floats of the stage's block in the constant row (even)
   return (op == RISP_OP_POLY10 || op == FOP_POLYG) ? 40 : (op == RISP_OP_GAMMA) ? 2 : (op == RISP_OP_GAIN) ? 4
-         : (op == RISP_OP_GTM) ? 8 : 0;
+         : (op == RISP_OP_GTM) ? 16 : 0;
 }
 __host__ __device__ constexpr int fop_nacc(int op) {    // float2 accumulators of the stage
   return (op == RISP_OP_POLY10 || op == FOP_POLYG) ? 30 : (op == RISP_OP_GAMMA) ? 1 : (op == RISP_OP_GAIN) ? 3
@@ -80,7 +80,7 @@ constexpr EffChain eff_of_sig() {
 template <unsigned SIG>
 struct Eff { static constexpr EffChain e = eff_of_sig<SIG>(); };
 
-constexpr int kCRowFloats = 64;   // one parameter row of derived constants (max over signatures: 40+2+4+8 = 54)
+constexpr int kCRowFloats = 64;   // one parameter row of derived constants (max over signatures: 40+2+4+16 = 62)
 constexpr int kCRows = 8;         // rows per slot: per-image parameter rows up to N = 8, else the interpreter kernel runs
 constexpr int kCSlots = 16;       // one slot per stream that uses the fused path (stream order makes reuse safe)
 
@@ -125,13 +125,15 @@ __device__ __forceinline__ P2 gamma_fwd(const P2& x, float gm, GammaSaved& sv) {
 }
 // d <- dL/dx (WITHOUT the factor gm when DEFER: the caller multiplies the upstream accumulators once at the end);
 // acc += d*y*lg2(xc)  (ln 2 applied in the epilogue).  rcp(x) may be inf/NaN where the mask is 0: selected away.
-template <bool IN01, bool NEED_DX, bool DEFER>
+// NOMASK: the caller applies the clamp mask itself (merged with the mask of the stage in front), so v is returned as is.
+template <bool IN01, bool NEED_DX, bool DEFER, bool NOMASK = false>
 __device__ __forceinline__ float2 gamma_bwd2(float2 x, float2 y, float2 l2, float2 d, float gm, float2& acc) {
   const float2 t = mul2(d, y);
   acc = fma2(t, l2, acc);
   if (!NEED_DX) return zero2();
   float2 v = mul2(t, make_float2(rcp_ftz(x.x), rcp_ftz(x.y)));
   if (!DEFER) v = mul2s(v, gm);
+  if (NOMASK) return v;
   const bool mx = IN01 ? (x.x >= RISP_GAMMA_EPS) : (x.x >= RISP_GAMMA_EPS && x.x <= 1.f);
   const bool my = IN01 ? (x.y >= RISP_GAMMA_EPS) : (x.y >= RISP_GAMMA_EPS && x.y <= 1.f);
   return sel2(mx, my, v);
@@ -210,15 +212,66 @@ __device__ __forceinline__ P2 poly_bwd(const PolySaved& sv, const P2& d, const f
 }
 
 // ---- 4-segment tone curve, input in [0,1] ------------------------------------------------------------------------
-// hinge form  f(x) = s0 x + sum_k ds_k max(x - x_k, 0), x_k = k/4  (identical to the reference's segment formula on
-// [0,1), tools_origin.py:429-435); x == 1 is the pass-through pixel (out = 1, slope 1, no knot gradient).
-// constant block: s0, ds1, ds2, ds3, (1 - s3), slow flag
-__device__ __forceinline__ float2 gtm_fwd2(float2 x, const float* c, float2 (&hd)[3], bool slow, float2& mask) {
+// Reference: tools_origin.py:429-435, out = (x - x_k) * slope_k + y_k on the half-open segment [x_k, x_k+1), x_k = k/4;
+// x == 1 lies in no segment: the pass-through pixel (out = 1, slope 1, no knot gradient).
+// constant block: s0, ds1, ds2, ds3, (1 - s3), slow flag, -, -, a_0..a_3, s_0..s_3   (a_k = y_k - x_k s_k)
+//
+// Table form (default): the segment of a pixel is looked up instead of being rebuilt from three hinges and four step
+// masks.  FFMA.RZ(x, 4, 2^20) leaves floor(4x) in bits 3..5 of the sum (ulp 1/8), LOP3 turns that into the address of an
+// 8-byte entry (a_k, s_k) of a 64-byte table in shared memory (entry 4: x == 1 -> pass-through; entry 7: NaN -> NaN),
+// one LDS.64 fetches it:  out = s_k x + a_k,  d out / d x = s_k.  3 + 1 instructions per pixel and channel instead of
+// 1.5 FADD2 + 3 FMNMX + 2 FFMA2 (forward) and 4 FSET + 2 FFMA2 (slope).  The knot gradients still come from the hinge sums
+// A_0 = sum d x, A_k = sum d max(x - x_k, 0), the hinge being ONE saturating add (x - x_k < 1: the upper clamp never acts).
+// The inference kernels keep the hinge form: they are bound by the memory system, and the dependent LDS in the middle of
+// every pixel's chain costs them 4 % (measured); the backward-carrying kernels are bound by instruction issue.
+#ifndef RISP_FUSED_NO_GTM_TABLE
+constexpr bool kGtmTable = true;
+#else
+constexpr bool kGtmTable = false;
+#endif
+constexpr int kGtmTableBytes = 64;
+__device__ __forceinline__ float2 gtm_lookup(float x, uint32_t tbl) {     // tbl: 64-byte aligned shared address
+  const uint32_t bits = __float_as_uint(__fmaf_rz(x, 4.f, 1048576.f));
+  const uint32_t addr = (bits & 0x38u) | tbl;
+  float2 v;
+  asm("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+// one lane fills the table of a tone-curve stage from its constant block
+__device__ __forceinline__ void gtm_table_fill(uint32_t tbl, const float* c) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float a = (k < 4) ? c[8 + k] : 0.f, s = (k < 4) ? c[12 + k] : 1.f;
+    asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(tbl + 8u * k), "f"(a), "f"(s) : "memory");
+  }
+}
+template <bool TABLE>
+__device__ __forceinline__ float2 gtm_hinge(float2 x, float2 hd, float xk) {
+  if constexpr (TABLE) return make_float2(__saturatef(x.x - xk), __saturatef(x.y - xk));
+  else return make_float2(fmaxf(hd.x, 0.f), fmaxf(hd.y, 0.f));
+}
+// sv: state for the backward sweep -- table form: sv[0] = slope of the pixel's segment; hinge form: sv[k] = x - x_{k+1}
+template <bool TABLE>
+__device__ __forceinline__ float2 gtm_fwd2(float2 x, const float* c, float2 (&sv)[3], bool slow, float2& mask, uint32_t tbl) {
+ if constexpr (TABLE) {
+  const float2 e0 = gtm_lookup(x.x, tbl), e1 = gtm_lookup(x.y, tbl);
+  sv[0] = make_float2(e0.y, e1.y);
+  float2 y;
+  if (!slow) {
+    y.x = __saturatef(fmaf(e0.y, x.x, e0.x)); y.y = __saturatef(fmaf(e1.y, x.y, e1.x));
+  } else {     // some knot outside [0,1]: the final clamp (:438) can be active, keep its mask
+    const float2 f = make_float2(fmaf(e0.y, x.x, e0.x), fmaf(e1.y, x.y, e1.x));
+    y = sat2(f);
+    mask = make_float2((f.x == y.x || x.x >= 1.f) ? 1.f : 0.f, (f.y == y.y || x.y >= 1.f) ? 1.f : 0.f);
+  }
+ return y;
+ } else {
+  float2 (&hd)[3] = sv;
   hd[0] = add2s(x, -0.25f); hd[1] = add2s(x, -0.5f); hd[2] = add2s(x, -0.75f);
   float2 f = mul2s(x, c[0]);
-  f = fma2s(c[1], make_float2(fmaxf(hd[0].x, 0.f), fmaxf(hd[0].y, 0.f)), f);
-  f = fma2s(c[2], make_float2(fmaxf(hd[1].x, 0.f), fmaxf(hd[1].y, 0.f)), f);
-  const float2 h3 = make_float2(fmaxf(hd[2].x, 0.f), fmaxf(hd[2].y, 0.f));
+  f = fma2s(c[1], gtm_hinge<false>(x, hd[0], 0.25f), f);
+  f = fma2s(c[2], gtm_hinge<false>(x, hd[1], 0.5f), f);
+  const float2 h3 = gtm_hinge<false>(x, hd[2], 0.75f);
   float2 y;
   if (!slow) {
     y.x = __saturatef(fmaf(c[3], h3.x, f.x)); y.y = __saturatef(fmaf(c[3], h3.y, f.y));
@@ -228,29 +281,39 @@ __device__ __forceinline__ float2 gtm_fwd2(float2 x, const float* c, float2 (&hd
     mask = make_float2((f.x == y.x || x.x >= 1.f) ? 1.f : 0.f, (f.y == y.y || x.y >= 1.f) ? 1.f : 0.f);
   }
   return y;
+ }
 }
-__device__ __forceinline__ P2 gtm_fwd(const P2& x, const float* c, GtmSaved& sv, bool slow) {
+template <bool TABLE>
+__device__ __forceinline__ P2 gtm_fwd(const P2& x, const float* c, GtmSaved& sv, bool slow, uint32_t tbl) {
   sv.x = x;
   P2 y;
-  y.b = gtm_fwd2(x.b, c, sv.hd[0], slow, sv.m.b); y.g = gtm_fwd2(x.g, c, sv.hd[1], slow, sv.m.g);
-  y.r = gtm_fwd2(x.r, c, sv.hd[2], slow, sv.m.r);
+  y.b = gtm_fwd2<TABLE>(x.b, c, sv.hd[0], slow, sv.m.b, tbl); y.g = gtm_fwd2<TABLE>(x.g, c, sv.hd[1], slow, sv.m.g, tbl);
+  y.r = gtm_fwd2<TABLE>(x.r, c, sv.hd[2], slow, sv.m.r, tbl);
   return y;
 }
 // accumulates A_0 = sum d x, A_k = sum d max(x - x_k, 0); the knot gradients are the second differences
 // 4 (A_{j-1} - 2 A_j + A_{j+1}) (hat basis = second difference of hinges; A_4 = 0 on [0,1]), formed in the epilogue.
 template <bool NEED_DX>
-__device__ __forceinline__ float2 gtm_bwd2(float2 x, const float2 (&hd)[3], float2 d, const float* c, float2* acc) {
+__device__ __forceinline__ float2 gtm_bwd2(float2 x, const float2 (&sv)[3], float2 d, const float* c, float2* acc) {
   acc[0] = fma2(d, x, acc[0]);
+ if constexpr (kGtmTable) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) acc[k + 1] = fma2(d, gtm_hinge<true>(x, x, 0.25f * (float)(k + 1)), acc[k + 1]);
+  if (!NEED_DX) return zero2();
+  return mul2(d, sv[0]);
+ } else {
+  const float2 (&hd)[3] = sv;
   float2 slope = make_float2(c[0], c[0]);
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const float2 st = make_float2(hd[k].x >= 0.f ? 1.f : 0.f, hd[k].y >= 0.f ? 1.f : 0.f);
-    acc[k + 1] = fma2(d, make_float2(fmaxf(hd[k].x, 0.f), fmaxf(hd[k].y, 0.f)), acc[k + 1]);
+    acc[k + 1] = fma2(d, gtm_hinge<false>(x, hd[k], 0.f), acc[k + 1]);
     if (NEED_DX) slope = fma2s(c[k + 1], st, slope);
   }
   if (!NEED_DX) return zero2();
   slope = fma2s(c[4], make_float2(x.x >= 1.f ? 1.f : 0.f, x.y >= 1.f ? 1.f : 0.f), slope);   // x == 1: slope -> 1
   return mul2(d, slope);
+ }
 }
 template <bool NEED_DX>
 __device__ __forceinline__ P2 gtm_bwd(const GtmSaved& sv, const P2& d0, const float* c, float2* acc, bool slow) {
