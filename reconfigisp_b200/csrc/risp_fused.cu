@@ -542,8 +542,9 @@ fused_kernel(FusedArgs a, ChainDesc d, const __grid_constant__ CUtensorMap tm_ra
     if constexpr (MODE != MODE_FWD) {
       // ---- backward-carrying kernels (issue-bound): 2-row records, a private window per row read with plain LDS ----
       // one row: read the window and the GT row, demosaic, chain, store
-      auto do_row = [&](auto odd_tag, int r, const uint32_t* wa, uint32_t gta) {
+      auto do_row = [&](auto odd_tag, auto slow_tag, int r, const uint32_t* wa, uint32_t gta) {
         constexpr bool ODD = decltype(odd_tag)::value;
+        constexpr bool slow = decltype(slow_tag)::value;     // shadows the run-time flag: the chain's branches on it fold away
         float w[WR][WC];
   #pragma unroll
         for (int j = 0; j < WR; ++j) {
@@ -580,7 +581,11 @@ fused_kernel(FusedArgs a, ChainDesc d, const __grid_constant__ CUtensorMap tm_ra
         }
       };
 
-      // iteration m computes rows r = ra + 2(m-1) (even) and r+1 (odd) from records m-1, m, m+1
+      // iteration m computes rows r = ra + 2(m-1) (even) and r+1 (odd) from records m-1, m, m+1.
+      // The loop exists twice, with the tone curve's slow flag (a knot outside [0,1]: final clamp active) as a compile-time
+      // constant: two uniform branches per pixel pair and channel would otherwise cut the chain into ~25 basic blocks per
+      // trip, and the scheduler cannot interleave the two pairs / the FMA-heavy and the ALU/XU phases across them.
+      auto rows_loop = [&](auto slow_tag) {
       for (int m = 1; m < nrec - 1; ++m) {
         const int r = ra + 2 * (m - 1);
         wait_rec(m + 1);
@@ -600,13 +605,15 @@ fused_kernel(FusedArgs a, ChainDesc d, const __grid_constant__ CUtensorMap tm_ra
   #pragma unroll
           for (int j = 0; j < WR; ++j) { we[j] = row_addr(r - HL + j); wo[j] = row_addr(r + 1 - HL + j); }
         }
-        do_row(std::false_type{}, r, we, recB + RC::RAWB);
-        do_row(std::true_type{}, r + 1, wo, recB + RC::RAWB + kStrip * 4);
+        do_row(std::false_type{}, slow_tag, r, we, recB + RC::RAWB);
+        do_row(std::true_type{}, slow_tag, r + 1, wo, recB + RC::RAWB + kStrip * 4);
         __syncwarp();                              // every lane has read record m-1: its slot may be refilled
         if (m - 1 + D < nrec) {
           if (elect_one()) issue(m - 1 + D);
         }
       }
+      };
+      if (slow) rows_loop(std::true_type{}); else rows_loop(std::false_type{});
     } else {
       // ---- inference kernel (memory-bound): RR-row records, one shared window per row pair, halo by shuffle ---------
       float w[WR + 1][WC];                                        // raw rows r-HL .. r+1+HL of the current row pair
