@@ -131,12 +131,10 @@ class SuperPruneFifteenDemosFourBayerTwo(nn.Module):
     @staticmethod
     def _dummy(par_list, idxs):
         """0 * sum(params) of pruned candidates: zero instead of missing gradients (:199-201)."""
-        z = None
-        for i in idxs:
-            if par_list[i].nelement() > 0:
-                t = par_list[i].sum() * 0.0
-                z = t if z is None else z + t
-        return z
+        live = [par_list[i].view(-1) for i in idxs if par_list[i].nelement() > 0]
+        if not live:
+            return None
+        return (live[0] if len(live) == 1 else torch.cat(live)).sum() * 0.0
 
     # ------------------------------------------------------------------------------------------------------
     def _fan_out(self, jobs):
@@ -232,11 +230,15 @@ class SuperPruneFifteenDemosFourBayerTwo(nn.Module):
             # sigmoid of ALL parameter logits of the step in one launch (one cat, one sigmoid; the per-candidate values are views)
             sizes = [p.nelement() for p in pars]
             sg_all = torch.sigmoid(torch.cat([p.view(-1) for p in pars if p.nelement()]))
-            offs, o = [], 0
-            for n_ in sizes:
-                offs.append(o)
-                o += n_
-            sig = lambda i: sg_all[offs[i]:offs[i] + sizes[i]].view(1, -1)
+            # one split instead of a slice per candidate: its backward is ONE cat of the candidates' gradients (a slice each
+            # costs a zero-fill, a copy and an accumulation add per candidate and pass)
+            parts = torch.split(sg_all, [n_ for n_ in sizes if n_])
+            slot, o = {}, 0
+            for i_, n_ in enumerate(sizes):
+                if n_:
+                    slot[i_] = o
+                    o += 1
+            sig = lambda i: parts[slot[i]].view(1, -1)
             # kernel-level parameter table of the classical candidates, one row per image:
             # [gamma | grayworld gains | wbmanual p*5 | wbquadratic p*10-5 | gtm knots]  (tools_origin.py:214, :326)
             gw = grayworld_gains(x) if not host[4] < 1e-9 else torch.ones((N, 3), device=x.device)

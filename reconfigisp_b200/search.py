@@ -73,20 +73,36 @@ class DartsModel:
         self.log_dict['loss'] = l_pix.detach()
 
     def virtual_step(self):
-        """pass #1: p' = p - lr_meta * (momentum * buf + g), written into netV; alphas copied (:182-222)."""
+        """pass #1: p' = p - lr_meta * (momentum * buf + g), written into netV; alphas copied (:182-222).
+        All parameter tensors move through multi-tensor (`torch._foreach_*`) launches: same arithmetic per element."""
         loss = self._loss(self.netG(self.img), self.gt)
         P = self.netG.trainable_parameters
         nz = [p for p in P if p.nelement() > 0]
         grads = iter(self._grads(loss, nz))
         with torch.no_grad():
+            ps, vps, gs, bufs, plain = [], [], [], [], []
             for p, vp in zip(P, self.netV.trainable_parameters):
                 if p.nelement() == 0:
                     continue
                 g = next(grads)
-                momentum = self.optimizer_G.state[p].get('momentum_buffer', 0.) * self.momentum_G
-                vp.copy_(p if g is None else p - self.lr_meta * (momentum + g))
-            for a, va in zip(self.netG.alphas, self.netV.alphas):
-                va.copy_(a)
+                if g is None:
+                    plain.append((p, vp))
+                    continue
+                ps.append(p)
+                vps.append(vp)
+                gs.append(g)
+                bufs.append(self.optimizer_G.state[p].get('momentum_buffer'))
+            if ps:
+                if all(b is not None for b in bufs):
+                    t = torch._foreach_mul(bufs, self.momentum_G)
+                    torch._foreach_add_(t, gs)                       # momentum + g
+                else:                                              # before the first optimizer step: buffers are 0.
+                    t = [g + (0. if b is None else b * self.momentum_G) for g, b in zip(gs, bufs)]
+                torch._foreach_mul_(t, self.lr_meta)
+                torch._foreach_copy_(vps, torch._foreach_sub(ps, t))
+            if plain:
+                torch._foreach_copy_([vp for _, vp in plain], [p for p, _ in plain])
+            torch._foreach_copy_(list(self.netV.alphas), list(self.netG.alphas))
 
     def optimize_alphas(self):
         """passes #1-#4 (:224-268)."""
@@ -100,13 +116,17 @@ class DartsModel:
         dalpha, dp = v_grads[:len(v_alphas)], v_grads[len(v_alphas):]
         hessian = self.compute_hessian(dp)
         with torch.no_grad():
-            for idx, (alpha, da, h) in enumerate(zip(self.netG.alphas, dalpha, hessian)):
-                if da is None or h is None:
+            live = [i for i, (da, h) in enumerate(zip(dalpha, hessian)) if da is not None and h is not None]
+            if live:
+                hs = [hessian[i] for i in live]
+                gs = torch._foreach_sub([dalpha[i] for i in live], torch._foreach_mul(hs, self.lr_meta))    # da - lr_meta * h
+            for idx, alpha in enumerate(self.netG.alphas):
+                if idx not in live:
                     alpha.grad = torch.zeros_like(alpha)
                 else:
                     # NaN guard (:260-263) without the host sync: where() on the device
-                    bad = torch.isnan(h).any()
-                    alpha.grad = torch.where(bad, torch.zeros_like(alpha), da - self.lr_meta * h)
+                    k = live.index(idx)
+                    alpha.grad = torch.where(torch.isnan(hs[k]).any(), 0., gs[k])
         self.optimizer_alpha.step()
 
     def compute_hessian(self, dp):
@@ -114,21 +134,26 @@ class DartsModel:
         nz = [p for p in self.netG.trainable_params if p.nelement() > 0]
         norm = torch.cat([w.reshape(-1) for w in dp if w is not None]).norm()
         eps = torch.where(norm < 1e-6, torch.zeros_like(norm), 0.01 / norm)          # device scalar, no sync
+        ps = [p for p, d in zip(nz, dp) if d is not None]
+        ds = [d for d in dp if d is not None]
         with torch.no_grad():
-            for p, d in zip(nz, dp):
-                if d is not None:
-                    p += eps * d
+            step = torch._foreach_mul(ds, eps)                  # eps * d
+            step2 = torch._foreach_mul(ds, 2. * eps)            # (2. * eps) * d
+            torch._foreach_add_(ps, step)
         dalpha_pos = self._grads(self._loss(self.netG(self.img), self.gt), self.netG.alphas)
         with torch.no_grad():
-            for p, d in zip(nz, dp):
-                if d is not None:
-                    p -= 2. * eps * d
+            torch._foreach_sub_(ps, step2)
         dalpha_neg = self._grads(self._loss(self.netG(self.img), self.gt), self.netG.alphas)
         with torch.no_grad():
-            for p, d in zip(nz, dp):
-                if d is not None:
-                    p += eps * d
-        return [(p - n) / 2. * eps if p is not None and n is not None else None for p, n in zip(dalpha_pos, dalpha_neg)]
+            torch._foreach_add_(ps, step)
+            live = [i for i, (p, n) in enumerate(zip(dalpha_pos, dalpha_neg)) if p is not None and n is not None]
+            h = torch._foreach_sub([dalpha_pos[i] for i in live], [dalpha_neg[i] for i in live])
+            torch._foreach_div_(h, 2.)
+            torch._foreach_mul_(h, eps)                         # (pos - neg) / 2. * eps
+        out = [None] * len(dalpha_pos)
+        for k, i in enumerate(live):
+            out[i] = h[k]
+        return out
 
     def test(self):
         self.output = self.netG(self.img)
