@@ -50,7 +50,7 @@ __global__ void fused_prep_kernel(const float* __restrict__ params, int pstride,
     float* o = c + e.coff[k];
     const float* q = p + d.off[e.src[k]];
     switch (e.op[k]) {
-      case RISP_OP_GAMMA: o[0] = q[0]; o[1] = 0.f; break;
+      case RISP_OP_GAMMA: o[0] = q[0]; o[1] = q[0] - 1.f; break;     // gm, gm - 1 (RFORM)
       case RISP_OP_GAIN: o[0] = q[0]; o[1] = q[1]; o[2] = q[2]; o[3] = 0.f; break;
       case RISP_OP_POLY10:
       case FOP_POLYG: {
@@ -293,11 +293,16 @@ struct Tail {
       if constexpr (OP == RISP_OP_SKIP) {
         return Tail<SIG, K + 1, MODE, C>::go(x, tgt, cp, acc, loss, yout, slow, lane_w, tbl);
       } else if constexpr (OP == RISP_OP_GAMMA) {
-        float2 l2;
+        float2 l2, r = zero2();
         const float gm = c[0];
-        const float2 y = gamma_fwd2<IN01>(x, gm, l2);
+#ifdef RISP_FUSED_RFORM      // measured: 2 % slower (the product y = r xc lengthens the dependent chain; the XU pipe is not the limiter)
+        constexpr bool RFORM = NEED_DX && MODE != MODE_FWD;
+#else
+        constexpr bool RFORM = false;
+#endif
+        const float2 y = gamma_fwd2<IN01, RFORM>(x, gm, l2, c[1], &r);
         const float2 d = Tail<SIG, K + 1, MODE, C>::go(y, tgt, cp, acc, loss, yout, slow, lane_w, tbl);
-        return gamma_bwd2<IN01, NEED_DX, true, NOMASK>(x, y, l2, d, gm, a[0]);
+        return gamma_bwd2<IN01, NEED_DX, true, NOMASK, RFORM>(x, y, l2, d, gm, a[0], r);
       } else if constexpr (OP == RISP_OP_GAIN) {
         const float2 y = mul2s(x, c[C]);
         const float2 d = Tail<SIG, K + 1, MODE, C>::go(y, tgt, cp, acc, loss, yout, slow, lane_w, tbl);

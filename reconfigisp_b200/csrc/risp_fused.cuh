@@ -107,14 +107,23 @@ struct GainSaved { P2 x; };
 struct GtmSaved { P2 x; float2 hd[3][3]; P2 m; };  // hd[c][k] = x_c - x_{k+1};  m = final-clamp mask (slow path only)
 
 // ---- gamma: y = clamp(x, eps, 1)^gm ------------------------------------------------------------------------------
-template <bool IN01>
-__device__ __forceinline__ float2 gamma_fwd2(float2 x, float gm, float2& l2) {
+// RFORM (the stage's input gradient is needed): y = xc * r with r = xc^(gm-1) = ex2((gm-1) lg2 xc).  The backward sweep then
+// has d y / d x = gm r without the reciprocal of the plain form (t / x): 2 MUFU per pixel and channel instead of 3.  Opt-in
+// (-DRISP_FUSED_RFORM): on the B200 the step kernel got 2 % SLOWER with it (0.294 -> 0.300 ms per 48 MP).
+template <bool IN01, bool RFORM = false>
+__device__ __forceinline__ float2 gamma_fwd2(float2 x, float gm, float2& l2, float gm1 = 0.f, float2* r = nullptr) {
   float2 xc;
   xc.x = IN01 ? fmaxf(x.x, RISP_GAMMA_EPS) : fminf(fmaxf(x.x, RISP_GAMMA_EPS), 1.f);
   xc.y = IN01 ? fmaxf(x.y, RISP_GAMMA_EPS) : fminf(fmaxf(x.y, RISP_GAMMA_EPS), 1.f);
   l2 = make_float2(lg2_ftz(xc.x), lg2_ftz(xc.y));
-  const float2 t = mul2s(l2, gm);
-  return make_float2(ex2_ftz(t.x), ex2_ftz(t.y));
+  if constexpr (RFORM) {
+    const float2 t = mul2s(l2, gm1);
+    *r = make_float2(ex2_ftz(t.x), ex2_ftz(t.y));
+    return mul2(*r, xc);
+  } else {
+    const float2 t = mul2s(l2, gm);
+    return make_float2(ex2_ftz(t.x), ex2_ftz(t.y));
+  }
 }
 template <bool IN01>
 __device__ __forceinline__ P2 gamma_fwd(const P2& x, float gm, GammaSaved& sv) {
@@ -126,12 +135,12 @@ __device__ __forceinline__ P2 gamma_fwd(const P2& x, float gm, GammaSaved& sv) {
 // d <- dL/dx (WITHOUT the factor gm when DEFER: the caller multiplies the upstream accumulators once at the end);
 // acc += d*y*lg2(xc)  (ln 2 applied in the epilogue).  rcp(x) may be inf/NaN where the mask is 0: selected away.
 // NOMASK: the caller applies the clamp mask itself (merged with the mask of the stage in front), so v is returned as is.
-template <bool IN01, bool NEED_DX, bool DEFER, bool NOMASK = false>
-__device__ __forceinline__ float2 gamma_bwd2(float2 x, float2 y, float2 l2, float2 d, float gm, float2& acc) {
+template <bool IN01, bool NEED_DX, bool DEFER, bool NOMASK = false, bool RFORM = false>
+__device__ __forceinline__ float2 gamma_bwd2(float2 x, float2 y, float2 l2, float2 d, float gm, float2& acc, float2 r = float2()) {
   const float2 t = mul2(d, y);
   acc = fma2(t, l2, acc);
   if (!NEED_DX) return zero2();
-  float2 v = mul2(t, make_float2(rcp_ftz(x.x), rcp_ftz(x.y)));
+  float2 v = RFORM ? mul2(d, r) : mul2(t, make_float2(rcp_ftz(x.x), rcp_ftz(x.y)));
   if (!DEFER) v = mul2s(v, gm);
   if (NOMASK) return v;
   const bool mx = IN01 ? (x.x >= RISP_GAMMA_EPS) : (x.x >= RISP_GAMMA_EPS && x.x <= 1.f);
