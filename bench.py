@@ -317,8 +317,11 @@ def run_tuning(args):
             ips = prof['step_thread_instr_per_px'] * px / (ms_k / 1e3)
             fp32 = {'bound': 'issue', 'achieved': round(ips / 1e12, 2), 'peak': round(SMS * 128 * SM_CLOCK_HZ / 1e12, 2), 'unit': 'T thread-instr/s',
                     'frac': round(ips / (SMS * 128 * SM_CLOCK_HZ), 4), 'thread_instr_per_px': prof['step_thread_instr_per_px'],
-                    'note': 'the step kernel is bound by instruction issue / the fp32 pipes, not by HBM: executed thread-instructions per '
-                            'pixel (ncu, static) x pixels / measured time vs 148 SMs x 128 lanes x 1.965 GHz'}
+                    'pipe_fma_pct_ncu': prof.get('step_pipe_fma_pct'), 'issue_active_pct_ncu': prof.get('step_issue_active_pct'),
+                    'note': 'the step kernel is bound by the fp32 pipe and the dependent chains of its 37-parameter stage stack, not by HBM: '
+                            'executed thread-instructions per pixel (ncu, static) x pixels / measured time vs 148 SMs x 128 lanes x 1.965 GHz; '
+                            'a packed FFMA2/FMUL2 holds the FMA pipe for two cycles (profiles/r2_fma_rates.txt), so the pipe is busier '
+                            'than the issue slots (pipe_fma_pct_ncu, static from the same capture)'}
         line = {'metric': METRIC, 'value': round(value, 1), 'unit': 'MP/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': round(ms_step, 4), 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',

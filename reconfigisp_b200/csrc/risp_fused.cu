@@ -438,6 +438,9 @@ __device__ __forceinline__ bool chain_slow(const float* __restrict__ cp) {
 #ifndef RISP_FUSED_FWD_MINB
 #define RISP_FUSED_FWD_MINB 16
 #endif
+#ifndef RISP_FUSED_FWD_MAXROWS
+#define RISP_FUSED_FWD_MAXROWS 256
+#endif
 
 template <int DM, int MODE, unsigned SIG>
 __global__ void __launch_bounds__(kWarps * 32, (MODE == MODE_FWD) ? RISP_FUSED_FWD_MINB : RISP_FUSED_STEP_MINB)
@@ -791,7 +794,7 @@ fused_kernel(FusedArgs a, ChainDesc d, const __grid_constant__ CUtensorMap tm_ra
 // ---- host side ---------------------------------------------------------------------------------------------------------
 struct Geometry { int rows_per_chunk, chunks, strip_blocks, cpf, grid; };
 
-static Geometry geometry(int N, int H, int W, int ctas_per_sm, int rr) {
+static Geometry geometry(int N, int H, int W, int ctas_per_sm, int rr, int max_rows = 256) {
   Geometry g;
   g.strip_blocks = (int)cdiv(W, kStrip);     // items are (row chunk, strip): one warp per CTA
   const int slots = sm_count() * ctas_per_sm;
@@ -799,7 +802,7 @@ static Geometry geometry(int N, int H, int W, int ctas_per_sm, int rr) {
   // rows per chunk: minimise rounds * (rows + per-item overhead); an item costs ~3 extra rows (window fill, exposed latency)
   long long best = -1;
   int best_rows = rr;
-  for (int rows = rr; rows <= 256; rows += rr) {        // whole records (rr rows each)
+  for (int rows = rr; rows <= max_rows; rows += rr) {        // whole records (rr rows each)
     if (rows > H && rows > rr) break;
     const int chunks = (int)cdiv(H, rows);
     const long long items = (long long)chunks * g.strip_blocks;
@@ -880,7 +883,10 @@ static int make_map(CUtensorMap* tm, const float* base, int W, int H, long long 
 
 template <int DM, int MODE, unsigned SIG>
 static int launch_one(FusedArgs a, const ChainDesc& d, int N, cudaStream_t st, Geometry* gout) {
-  const Geometry g = geometry(N, a.H, a.W, resident_ctas<DM, MODE, SIG>(), RingCfg<MODE>::RR);
+  // RISP_FUSED_FWD_ROWS / RISP_FUSED_STEP_ROWS: cap of the rows per item (experiments on the write order of the inference kernels)
+  static const int cap = [] { const char* e = getenv(MODE == MODE_FWD ? "RISP_FUSED_FWD_ROWS" : "RISP_FUSED_STEP_ROWS"); return e ? atoi(e) : 0; }();
+  const Geometry g = geometry(N, a.H, a.W, resident_ctas<DM, MODE, SIG>(), RingCfg<MODE>::RR,
+                              cap >= RingCfg<MODE>::RR ? cap : (MODE == MODE_FWD ? RISP_FUSED_FWD_MAXROWS : 256));
   if (gout) { *gout = g; return RISP_OK; }
   a.rows_per_chunk = g.rows_per_chunk; a.chunks = g.chunks; a.strip_blocks = g.strip_blocks; a.cpf = g.cpf;
   CUtensorMap tm_raw, tm_gt;
