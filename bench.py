@@ -443,8 +443,8 @@ def run_search(args):
                 'gpu_launches_note': '%d kernels of this library per iteration (counted by risp_launch_count)' % own_launches,
                 'roofline': {'bound': 'tensor', 'achieved': round(useful_tf, 1), 'peak': round(tf32_peak, 1), 'unit': 'TFLOP/s', 'frac': round(useful_tf / tf32_peak, 4),
                              'traffic': None, 'kernel': 'risp::conv_tc_kernel 64->64 3x3, %dx%dx%d (tcgen05 kind::tf32)' % (B, S, S), 'ms_per_launch': round(ms_c, 4),
-                             'note': 'useful fp32-equivalent FLOPs (2*Cin*Cout*K^2 per px) vs dense TF32 peak = measured bf16 peak / 2; the kernel issues 3x '
-                                     'that work (hi/lo split) to stay fp32-accurate'},
+                             'note': 'useful fp32-equivalent FLOPs (2*Cin*Cout*K^2 per px) vs dense TF32 peak = measured bf16 peak / 2; the kernel issues two MMAs '
+                                     'per 8 channels (kind::tf32 main term + one bf16 kind::f16 MMA for both cross terms of the hi/lo split) to stay fp32-accurate'},
                 'mixed_op': mixed}
     if rank == 0 and world == 1 and not args.no_cpu:
         rate, cores, dt = cpu_search_rate(4, 96, 2)
