@@ -226,3 +226,42 @@ def test_uint8_pack_and_crop_decode(ops):
     assert torch.equal(crop.cpu(), codes[:, :, 12:44, 34:74].float() / 16383.)
     with pytest.raises(ValueError):
         ops.crop_decode(codes.cuda(), 13, 34, 32, 40, 16383.)        # odd origin breaks the CFA phase
+
+
+@pytest.mark.parametrize('kind', ['nearest', 'bilinear'])
+def test_fused_tone_curve_pixels_exactly_on_knots(ops, kind):
+    """The backward-carrying kernels look the tone curve's segment up from floor(4x) (FFMA.RZ / LOP3 / LDS.64 table).  Frames
+    whose pixels sit EXACTLY on the knots 0, 1/4, 1/2, 1 (gamma = 1 passes powers of two through lg2 / ex2 unchanged) must pick
+    the upper segment like the reference's half-open `(x >= start) & (x < end)` (tools_origin.py:435) and treat x == 1 as the
+    pass-through pixel; the four segment slopes are made very different so that a wrong pick moves the gamma gradient."""
+    N, H, W = 2, 12, 264
+    g = torch.Generator().manual_seed(31)
+    vals = torch.tensor([0.0, 0.25, 0.5, 1.0, 0.125, 0.0625])
+    raw = vals[torch.randint(0, len(vals), (N, 1, H, W), generator=g)]
+    gt = torch.rand(N, 3, H, W, generator=g)
+    st = SIGS['D']
+    chain = ops.Chain(st)
+    params = torch.tensor([[1.0, 0.1, 0.7, 0.8]])
+    po = params.double().requires_grad_()
+    yo = oracle_chain(DM[kind](raw.double()), st, po.expand(N, -1))
+    lo = O.mse(yo, gt.double())
+    dpo, = torch.autograd.grad(lo, po)
+    yg = ops.pipeline_fwd(raw.cuda(), kind, chain, params.cuda())
+    assert float((yg.cpu().double() - yo.detach()).abs().max()) <= TOL
+    pg = params.cuda().requires_grad_()
+    lg = ops.pipeline_mse(pg, raw.cuda(), gt.cuda(), kind, chain)
+    dpg, = torch.autograd.grad(lg, pg)
+    assert abs(float(lg.detach()) - float(lo.detach())) <= 1e-5
+    relclose(dpg, dpo, rtol=1e-3)
+    # the same frames through the 37-parameter chain (identity polynomial, unit gains): the tone curve sits behind gamma there
+    stA = SIGS['A']
+    chainA = ops.Chain(stA)
+    pA = torch.tensor([[1.0, 1.0, 1.0] + IDENT + [1.0, 0.1, 0.7, 0.8]])
+    poA = pA.double().requires_grad_()
+    loA = O.mse(oracle_chain(DM[kind](raw.double()), stA, poA.expand(N, -1)), gt.double())
+    dpoA, = torch.autograd.grad(loA, poA)
+    pgA = pA.cuda().requires_grad_()
+    lgA = ops.pipeline_mse(pgA, raw.cuda(), gt.cuda(), kind, chainA)
+    dpgA, = torch.autograd.grad(lgA, pgA)
+    assert abs(float(lgA.detach()) - float(loA.detach())) <= 1e-5
+    relclose(dpgA, dpoA, rtol=1e-3)
