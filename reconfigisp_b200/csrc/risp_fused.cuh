@@ -278,9 +278,15 @@ __device__ __forceinline__ float2 gtm_fwd2(float2 x, const float* c, float2 (&sv
   float2 (&hd)[3] = sv;
   hd[0] = add2s(x, -0.25f); hd[1] = add2s(x, -0.5f); hd[2] = add2s(x, -0.75f);
   float2 f = mul2s(x, c[0]);
-  f = fma2s(c[1], gtm_hinge<false>(x, hd[0], 0.25f), f);
-  f = fma2s(c[2], gtm_hinge<false>(x, hd[1], 0.5f), f);
-  const float2 h3 = gtm_hinge<false>(x, hd[2], 0.75f);
+  // hinge as ONE saturating add (x - x_k < 1): -DRISP_FUSED_FWD_MAXHINGE restores the packed add + FMNMX form
+#ifndef RISP_FUSED_FWD_MAXHINGE
+  constexpr bool SATH = true;
+#else
+  constexpr bool SATH = false;
+#endif
+  f = fma2s(c[1], gtm_hinge<SATH>(x, hd[0], 0.25f), f);
+  f = fma2s(c[2], gtm_hinge<SATH>(x, hd[1], 0.5f), f);
+  const float2 h3 = gtm_hinge<SATH>(x, hd[2], 0.75f);
   float2 y;
   if (!slow) {
     y.x = __saturatef(fmaf(c[3], h3.x, f.x)); y.y = __saturatef(fmaf(c[3], h3.y, f.y));
