@@ -450,6 +450,7 @@ fused_kernel(FusedArgs a, ChainDesc d, const __grid_constant__ CUtensorMap tm_ra
   constexpr int WR = 2 * HL + 1, WC = 4 + 2 * HL;
   constexpr int NACC = (MODE == MODE_FWD || E.nacc == 0) ? 1 : E.nacc;
   constexpr int NCST = E.ncst > 0 ? E.ncst : 1;
+  static_assert(E.ncst <= kCRowFloats, "the chain's derived constants must fit one row of the constant slot");
   constexpr bool PKDM = E.n > 0 && (E.op[0] == RISP_OP_POLY10 || E.op[0] == FOP_POLYG || E.op[0] == RISP_OP_GAIN);
   using RC = RingCfg<MODE>;
   constexpr int D = RC::D;
